@@ -1,0 +1,338 @@
+"""ctypes binding of include/sf_b200.h (libsf_b200.so).  Host-side mirror of the reference's
+solver-facing interface: `SPHSolver` carries the method names of QtSPHSolver
+(/root/reference/Include/QtSPHSolver.h:27-36) and SPHSolver<float> (Source/Simulator.cpp:42,49)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, "csrc")
+_LIB_PATH = os.path.join(_HERE, "lib", "libsf_b200.so")
+
+SCENES = {"SphereDrop": 0, "CubeDrop": 1, "Dambreak": 2, "DoubleDambreak": 3}  # Include/Common.h:52-58
+
+FIELD_DENSITY, FIELD_PRESSURE, FIELD_ACCEL, FIELD_CELL_INDEX, FIELD_NEIGHBOR_COUNT, FIELD_NEIGHBOR_IDS, \
+    FIELD_SORT_PERM, FIELD_TABLE_CUBIC_W, FIELD_TABLE_SPIKY_GRAD = range(9)
+
+EXPORTS = [
+    "sf_params_default", "sf_params_set_resolution", "sf_params_update", "sf_scene_generate", "sf_build_tables",
+    "sf_boundary_generate", "sf_create", "sf_destroy",
+    "sf_set_params", "sf_get_params", "sf_last_error", "sf_set_stream", "sf_upload_particles", "sf_num_particles",
+    "sf_download_positions", "sf_download_velocities", "sf_generate_boundary", "sf_set_boundary_particles",
+    "sf_get_boundary_particles", "sf_make_ready", "sf_advance_frame", "sf_advance_steps", "sf_advance_frame_time",
+    "sf_synchronize", "sf_step_host", "sf_set_capture", "sf_field_size", "sf_download_field", "sf_grid_dims",
+    "sf_profile_enable", "sf_profile_reset", "sf_profile_get", "sf_launch_count", "sf_timer_start", "sf_timer_stop",
+    "sf_comm_unique_id", "sf_comm_init", "sf_upload_particles_global", "sf_slab_info", "sf_download_owned",
+]
+
+
+class SFError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"sf_b200 error {code}: {msg}")
+        self.code = code
+
+
+class SFParams(C.Structure):
+    """struct sf_params (= SPHParameters<float>, Source/Controller.cpp:54-63)."""
+    _fields_ = [
+        ("scene", C.c_int32), ("numThreads", C.c_int32), ("stopTime", C.c_float), ("defaultTimestep", C.c_float),
+        ("boxMin", C.c_float * 3), ("boxMax", C.c_float * 3),
+        ("pressureStiffness", C.c_float), ("viscosity", C.c_float), ("kernelRadius", C.c_float),
+        ("bCorrectDensity", C.c_int32), ("bUseBoundaryParticles", C.c_int32), ("bUseAttractivePressure", C.c_int32),
+        ("boundaryRestitution", C.c_float), ("attractivePressureRatio", C.c_float), ("restDensity", C.c_float),
+        ("particleMass", C.c_float), ("particleRadius", C.c_float), ("kernelRadiusSqr", C.c_float),
+        ("restDensitySqr", C.c_float),
+    ]
+
+    def updateParams(self):
+        library().sf_params_update(C.byref(self))
+
+
+def library_path():
+    return _LIB_PATH
+
+
+def build_library(force=False, verbose=False):
+    """Compile libsf_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+    args = ["make", "-C", _CSRC, "--no-print-directory"]
+    if force:
+        args.append("-B")
+    r = subprocess.run(args, capture_output=True, text=True)
+    if verbose or r.returncode:
+        print(r.stdout + r.stderr)
+    if r.returncode:
+        raise RuntimeError("building libsf_b200.so failed")
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def library():
+    """Load the C-ABI library.  Fails loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise SFError(-2, f"{_LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU fallback)")
+    L = C.CDLL(_LIB_PATH)
+    vp, i32, u32, u64, f32 = C.c_void_p, C.c_int32, C.c_uint32, C.c_uint64, C.c_float
+    PP = C.POINTER(SFParams)
+    sig = {
+        "sf_params_default": [PP], "sf_params_set_resolution": [PP, f32], "sf_params_update": [PP],
+        "sf_scene_generate": [PP, C.c_int, vp, u64, C.POINTER(u64)],
+        "sf_build_tables": [PP, vp, vp, vp], "sf_boundary_generate": [PP, u32, C.c_int, vp, u32, C.POINTER(u32)],
+        "sf_create": [PP, C.c_int, C.POINTER(vp)], "sf_set_params": [vp, PP], "sf_get_params": [vp, PP],
+        "sf_set_stream": [vp, vp], "sf_upload_particles": [vp, vp, vp, u32], "sf_num_particles": [vp, C.POINTER(u32)],
+        "sf_download_positions": [vp, vp], "sf_download_velocities": [vp, vp], "sf_generate_boundary": [vp, u32],
+        "sf_set_boundary_particles": [vp, C.c_int, vp, u32],
+        "sf_get_boundary_particles": [vp, C.c_int, vp, u32, C.POINTER(u32)],
+        "sf_make_ready": [vp], "sf_advance_frame": [vp, C.POINTER(f32)], "sf_advance_steps": [vp, u32, C.POINTER(f32)],
+        "sf_advance_frame_time": [vp, C.c_double, C.POINTER(f32), C.POINTER(u32)], "sf_synchronize": [vp],
+        "sf_step_host": [vp, vp, vp, u32, C.POINTER(f32)], "sf_set_capture": [vp, C.c_int],
+        "sf_field_size": [vp, C.c_int, C.POINTER(u64)], "sf_download_field": [vp, C.c_int, vp, u64],
+        "sf_grid_dims": [vp, C.POINTER(i32)], "sf_profile_enable": [vp, C.c_int], "sf_profile_reset": [vp],
+        "sf_profile_get": [vp, vp, C.c_size_t, vp, vp, u32, C.POINTER(u32)], "sf_launch_count": [vp, C.POINTER(u64)],
+        "sf_timer_start": [vp], "sf_timer_stop": [vp, C.POINTER(f32)],
+        "sf_comm_unique_id": [vp], "sf_comm_init": [vp, C.c_int, C.c_int, vp],
+        "sf_upload_particles_global": [vp, vp, vp, u32],
+        "sf_slab_info": [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(u32), C.POINTER(u32)],
+        "sf_download_owned": [vp, vp, vp, vp, u32, C.POINTER(u32)],
+    }
+    for name, argtypes in sig.items():
+        fn = getattr(L, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+    L.sf_destroy.argtypes = [vp]
+    L.sf_destroy.restype = None
+    L.sf_last_error.argtypes = [vp]
+    L.sf_last_error.restype = C.c_char_p
+    _lib = L
+    return L
+
+
+def default_params(resolution=24.0, scene="Dambreak", **overrides):
+    """SPHParameters defaults + Controller::updateSimParams (Source/Controller.cpp:52-64)."""
+    p = SFParams()
+    L = library()
+    L.sf_params_default(C.byref(p))
+    p.scene = SCENES[scene] if isinstance(scene, str) else int(scene)
+    L.sf_params_set_resolution(C.byref(p), C.c_float(resolution))
+    for k, v in overrides.items():
+        setattr(p, k, v)
+    L.sf_params_update(C.byref(p))
+    return p
+
+
+def scene_generate(params, scene=None):
+    """SceneManager::setupScene (Source/SceneManager.cpp:21-38): (N,3) float32 positions; velocities are zero."""
+    L = library()
+    sid = params.scene if scene is None else (SCENES[scene] if isinstance(scene, str) else int(scene))
+    n = C.c_uint64(0)
+    L.sf_scene_generate(C.byref(params), sid, None, 0, C.byref(n))
+    out = np.empty((n.value, 3), np.float32)
+    L.sf_scene_generate(C.byref(params), sid, out.ctypes.data, n.value, C.byref(n))
+    return out
+
+
+def build_tables(params):
+    """(cubicW[10001], spikyGrad[10001], (W_zero, radius2, invStep)) as makeReady() builds them."""
+    w, g, c = np.empty(10001, np.float32), np.empty(10001, np.float32), np.empty(3, np.float32)
+    library().sf_build_tables(C.byref(params), w.ctypes.data, g.ctypes.data, c.ctypes.data)
+    return w, g, c
+
+
+def boundary_generate(params, seed, wall):
+    n = C.c_uint32(0)
+    library().sf_boundary_generate(C.byref(params), seed, wall, None, 0, C.byref(n))
+    out = np.empty((n.value, 3), np.float32)
+    library().sf_boundary_generate(C.byref(params), seed, wall, out.ctypes.data, n.value, C.byref(n))
+    return out
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):  # torch tensor (pinned host memory in bench.py)
+        return a.data_ptr()
+    return a
+
+
+class SPHSolver:
+    """Mirror of QtSPHSolver : SPHSolver<float>.  Method names follow the reference."""
+
+    def __init__(self, params, device=0):
+        self.L = library()
+        self.params = params
+        h = C.c_void_p()
+        rc = self.L.sf_create(C.byref(params), device, C.byref(h))
+        if rc:
+            raise SFError(rc, (self.L.sf_last_error(None) or b"").decode())
+        self.h = h
+
+    # -- plumbing
+    def _ck(self, rc):
+        if rc:
+            raise SFError(rc, (self.L.sf_last_error(self.h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.sf_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- reference surface
+    def setParticles(self, pos, vel=None):
+        """What SceneManager::setupScene does to getParticles()/getVelocity() (Source/Simulator.cpp:95)."""
+        pos = np.ascontiguousarray(pos, np.float32)
+        vel = None if vel is None else np.ascontiguousarray(vel, np.float32)
+        self._ck(self.L.sf_upload_particles(self.h, _ptr(pos), _ptr(vel), pos.shape[0]))
+
+    def setupScene(self, scene=None):
+        pos = scene_generate(self.params, scene)
+        self.setParticles(pos)
+        return pos
+
+    def getNumParticles(self):
+        n = C.c_uint32(0)
+        self._ck(self.L.sf_num_particles(self.h, C.byref(n)))
+        return n.value
+
+    def getParticles(self):
+        out = np.empty((self.getNumParticles(), 3), np.float32)
+        self._ck(self.L.sf_download_positions(self.h, out.ctypes.data))
+        return out
+
+    def getVelocity(self):
+        out = np.empty((self.getNumParticles(), 3), np.float32)
+        self._ck(self.L.sf_download_velocities(self.h, out.ctypes.data))
+        return out
+
+    def generateBoundaryParticles(self, seed=0):
+        self._ck(self.L.sf_generate_boundary(self.h, seed))
+
+    def setBoundaryParticles(self, wall, xyz):
+        xyz = np.ascontiguousarray(xyz, np.float32)
+        self._ck(self.L.sf_set_boundary_particles(self.h, wall, xyz.ctypes.data, xyz.shape[0]))
+
+    def getBoundaryParticles(self, wall):
+        n = C.c_uint32(0)
+        self._ck(self.L.sf_get_boundary_particles(self.h, wall, None, 0, C.byref(n)))
+        out = np.empty((n.value, 3), np.float32)
+        self._ck(self.L.sf_get_boundary_particles(self.h, wall, out.ctypes.data, n.value, C.byref(n)))
+        return out
+
+    def makeReady(self):
+        self._ck(self.L.sf_make_ready(self.h))
+
+    def advanceFrame(self):
+        """One substep; returns the dt advanced (Source/Simulator.cpp:49)."""
+        dt = C.c_float(0)
+        self._ck(self.L.sf_advance_frame(self.h, C.byref(dt)))
+        return dt.value
+
+    # -- extensions of the C-ABI
+    def advanceSteps(self, n, want_time=False):
+        if want_time:
+            t = C.c_float(0)
+            self._ck(self.L.sf_advance_steps(self.h, n, C.byref(t)))
+            return t.value
+        self._ck(self.L.sf_advance_steps(self.h, n, None))
+        return None
+
+    def advanceFrameTime(self, frame_time=0.0333333333):
+        t, k = C.c_float(0), C.c_uint32(0)
+        self._ck(self.L.sf_advance_frame_time(self.h, frame_time, C.byref(t), C.byref(k)))
+        return t.value, k.value
+
+    def synchronize(self):
+        self._ck(self.L.sf_synchronize(self.h))
+
+    def stepHost(self, pos, vel):
+        dt = C.c_float(0)
+        n = pos.shape[0]
+        self._ck(self.L.sf_step_host(self.h, _ptr(pos), _ptr(vel), n, C.byref(dt)))
+        return dt.value
+
+    def setStream(self, cuda_stream_ptr):
+        self._ck(self.L.sf_set_stream(self.h, cuda_stream_ptr))
+
+    def setCapture(self, on=True):
+        self._ck(self.L.sf_set_capture(self.h, 1 if on else 0))
+
+    def gridDims(self):
+        d = (C.c_int32 * 3)()
+        self._ck(self.L.sf_grid_dims(self.h, d))
+        return tuple(d)
+
+    def field(self, field):
+        nbytes = C.c_uint64(0)
+        self._ck(self.L.sf_field_size(self.h, field, C.byref(nbytes)))
+        dtype = np.uint32 if field in (FIELD_CELL_INDEX, FIELD_NEIGHBOR_COUNT, FIELD_NEIGHBOR_IDS, FIELD_SORT_PERM) else np.float32
+        out = np.empty(nbytes.value // 4, dtype)
+        if nbytes.value:
+            self._ck(self.L.sf_download_field(self.h, field, out.ctypes.data, nbytes.value))
+        if field == FIELD_ACCEL:
+            out = out.reshape(-1, 3)
+        return out
+
+    def density(self):
+        return self.field(FIELD_DENSITY)
+
+    def pressure(self):
+        return self.field(FIELD_PRESSURE)
+
+    def accel(self):
+        return self.field(FIELD_ACCEL)
+
+    def cellIndex(self):
+        return self.field(FIELD_CELL_INDEX)
+
+    def neighbors(self):
+        return self.field(FIELD_NEIGHBOR_COUNT), self.field(FIELD_NEIGHBOR_IDS)
+
+    # -- measurement
+    def profileEnable(self, on=True):
+        self._ck(self.L.sf_profile_enable(self.h, 1 if on else 0))
+
+    def profileReset(self):
+        self._ck(self.L.sf_profile_reset(self.h))
+
+    def profile(self):
+        cap = 64
+        names = C.create_string_buffer(4096)
+        ms = (C.c_double * cap)()
+        launches = (C.c_uint64 * cap)()
+        count = C.c_uint32(0)
+        self._ck(self.L.sf_profile_get(self.h, names, 4096, ms, launches, cap, C.byref(count)))
+        parts = names.raw.split(b"\0")
+        return {parts[i].decode(): (ms[i], launches[i]) for i in range(count.value)}
+
+    def launchCount(self):
+        n = C.c_uint64(0)
+        self._ck(self.L.sf_launch_count(self.h, C.byref(n)))
+        return n.value
+
+    def timerStart(self):
+        self._ck(self.L.sf_timer_start(self.h))
+
+    def timerStop(self):
+        ms = C.c_float(0)
+        self._ck(self.L.sf_timer_stop(self.h, C.byref(ms)))
+        return ms.value

@@ -1,0 +1,71 @@
+// sf_device.cuh -- device-side data model of the B200 SPH step.
+//
+// HBM layout (all SoA, one entry per particle slot, fp32 / uint32):
+//   posA/velA/idA : state at the start of a substep, in the sorted order of the PREVIOUS substep
+//                   (float4 {x,y,z,-}, float4 {vx,vy,vz,-}, original particle id)
+//   keys/vals[2]  : radix-sort ping-pong (cell key, slot in A)
+//   posB/velB/idB : state re-sorted by cell key for THIS substep.  The .w lanes carry the
+//                   per-particle terms the pair loops need so that every neighbour costs one
+//                   128-bit load:  posB.w = P(rho)/rho^2 (pressure term), velB.w = 1/rho
+//   keyB          : cell key per sorted slot ((cz*ny+cy)*nx+cx, reference A.7)
+//   cellTab       : uint2 {begin,end} sorted-slot range per cell, {0,0} when empty
+//   rho           : density per sorted slot
+//   nbrJ/nbrIdx   : neighbour list built once per substep by the density pass and reused by the
+//                   force and viscosity passes: ELL layout [k][slot] (row stride npad) so a warp
+//                   reads/writes 128 B rows; nbrJ = neighbour slot (or wall-particle index),
+//                   nbrIdx = kernel-table index min(trunc(sqrt(d2)*invStep), 10000) shared by the
+//                   cubic-W and spiky-grad tables
+//   nbrCnt        : packed counts: fluid (14 bit) | wallX (6) | wallY (6) | wallZ (6)
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace sf
+{
+struct DevParams {
+    float bmin[3], bmax[3];
+    float h, h2, r, mass, stiffness, viscosity, restitution, rho0, attractRatio;
+    float rhoMin, rhoMax; // f((double)rho0*0.1), f((double)rho0*10.0)
+    float Wzero, invStep, radius2;
+    float dtMin, dtMax;   // defaultTimestep*0.1f, defaultTimestep*10.0f
+    int   nx, ny, nz;
+    int   useBoundary, attractive, correctDensity, capture;
+    uint32_t n, npad;
+    int      kmax;
+    uint32_t nbnd[6];     // wall particle counts
+    uint32_t bndStride;   // slots per wall in the bnd array
+};
+
+struct DevState {
+    unsigned maxv2Bits[2]; // max |v|^2 as float bits, ping-pong by step parity
+    float    dt;
+    unsigned step;
+    float    frameTime;   // accumulated like `frameTime += advanceFrame()` (Simulator.cpp:49)
+    unsigned skip;        // 1: frame target reached, the kernels of this substep are no-ops
+    double   frameTarget; // 0: no target
+    unsigned errFlags;    // SF_DEVERR_*
+    unsigned nbrMax;      // largest neighbour count seen (diagnostics)
+    unsigned long long stepsDone;
+};
+
+enum : unsigned { SF_DEVERR_NBR_OVERFLOW = 1u, SF_DEVERR_WALL_OVERFLOW = 2u };
+
+struct DevBuffers {
+    float4 *posA, *velA, *posB, *velB;
+    uint32_t *idA, *idB;
+    uint32_t *keys[2], *vals[2];
+    uint32_t *keyB;       // aliases the sorted keys buffer
+    uint2*    cellTab;
+    float*    rho;
+    float*    rho2;       // correctDensity scratch
+    float4*   accel;      // capture only
+    uint32_t* nbrJ;
+    uint16_t* nbrIdx;
+    uint32_t* nbrCnt;
+    float *tabW, *tabG;   // kTableEntries each
+    float4*   bnd;        // [6][bndStride]
+    uint32_t* radixCounts;
+    uint32_t* radixTotals;
+    DevState* state;
+};
+} // namespace sf
