@@ -1,0 +1,117 @@
+"""CPU tests of the product's host side: the C-ABI library loads and exports every symbol declared
+in include/sf_b200.h, and its host-side setup (parameters, scenes, kernel tables, wall particles)
+agrees bit for bit with the golden vectors and the oracle.  No compute calls without a GPU."""
+import ctypes as C
+import hashlib
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "sf_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sf_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(sf):
+    lib = C.CDLL(sf.library_path())
+    names = declared_symbols()
+    assert len(names) >= 35
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    from simplefluid_b200 import binding
+    assert set(binding.EXPORTS) == set(names)
+
+
+def test_params_defaults_and_update(sf, ob):
+    p, po = sf.default_params(24, "Dambreak"), ob.default_params(24, "Dambreak")
+    for name, _ in sf.SFParams._fields_:
+        a, b = getattr(p, name), getattr(po, name)
+        if hasattr(a, "__len__"):
+            assert list(a) == list(b), name
+        else:
+            assert a == b, name
+    p.kernelRadius = 2.0 / 64.0
+    p.updateParams()
+    po = ob.default_params(64, "Dambreak")
+    assert p.particleMass == po.particleMass and p.particleRadius == po.particleRadius and p.kernelRadiusSqr == po.kernelRadiusSqr
+
+
+@pytest.mark.parametrize("res", [24, 48, 100])
+@pytest.mark.parametrize("scene", ["SphereDrop", "CubeDrop", "Dambreak", "DoubleDambreak"])
+def test_scene_generate_matches_reference_golden(sf, scene, res):
+    with open(os.path.join(HERE, "golden", "scene_checksums.json")) as f:
+        g = json.load(f)["scenes"][f"{scene}@{res}"]
+    pos = sf.scene_generate(sf.default_params(res, scene))
+    assert len(pos) == g["n"]
+    assert hashlib.sha256(pos.tobytes()).hexdigest() == g["sha256"]
+
+
+def test_scene_generate_count_query_and_truncation(sf):
+    p = sf.default_params(24, "CubeDrop")
+    n = C.c_uint64(0)
+    assert sf.library().sf_scene_generate(C.byref(p), 1, None, 0, C.byref(n)) == 0 and n.value == 13824
+    buf = np.full((10, 3), 7.0, np.float32)
+    assert sf.library().sf_scene_generate(C.byref(p), 1, buf.ctypes.data, 5, C.byref(n)) == 0 and n.value == 13824
+    assert np.all(buf[5:] == 7.0) and np.all(buf[:5] != 7.0)
+    assert sf.library().sf_scene_generate(C.byref(p), 9, None, 0, C.byref(n)) != 0
+
+
+@pytest.mark.parametrize("res", [24, 61, 100, 203])
+def test_kernel_tables_match_oracle(sf, ob, res):
+    from simplefluid_b200 import binding
+    w, g, c = binding.build_tables(sf.default_params(res, "Dambreak"))
+    orc = ob.Oracle(ob.default_params(res, "Dambreak"), np.zeros((1, 3), np.float32), boundary_seed=0)
+    assert np.array_equal(w, orc.table(0)) and np.array_equal(g, orc.table(1))
+    assert np.array_equal(c, orc.kernel_consts()[:3])
+    assert w[10000] == 0 and g[10000] == 0 and g[0] == 0 and w[0] == c[0]
+    assert np.all(np.diff(w[:10000]) <= 0) and np.all(g[1:10000] <= 0)  # W decreasing, spiky gradient attractive sign
+    orc.close()
+
+
+@pytest.mark.parametrize("seed", [0, 1, 12345])
+def test_boundary_particles_match_oracle(sf, ob, seed):
+    from simplefluid_b200 import binding
+    p, po = sf.default_params(24, "Dambreak"), ob.default_params(24, "Dambreak")
+    orc = ob.Oracle(po, np.zeros((1, 3), np.float32), boundary_seed=seed)
+    for wall in range(6):
+        b = binding.boundary_generate(p, seed, wall)
+        assert b.shape == (243, 3)  # 9 x 9 x 3 for every resolution (A.4)
+        assert np.array_equal(b, orc.boundary(wall))
+        axis, upper = wall // 2, wall & 1
+        assert np.all(b[:, axis] > 1.0) if upper else np.all(b[:, axis] < -1.0)  # patches hang outside the box
+    orc.close()
+
+
+def test_no_cpu_fallback(sf):
+    """Without a usable B200 the product must refuse loudly, never compute on the host."""
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("GPU present")
+    with pytest.raises(sf.SFError) as e:
+        sf.SPHSolver(sf.default_params(24, "Dambreak"))
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_product_does_not_reference_oracle():
+    """The oracle is test infrastructure: nothing under simplefluid_b200/ or include/ may mention it."""
+    bad = []
+    for base in ("simplefluid_b200", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, base)):
+            for fn in files:
+                if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp", "Makefile")):
+                    text = open(os.path.join(dirpath, fn), errors="ignore").read()
+                    if re.search(r"sf_oracle|oracle_binding|libsf_oracle|sfo_", text):
+                        bad.append(os.path.join(dirpath, fn))
+    assert not bad, bad
