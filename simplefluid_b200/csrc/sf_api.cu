@@ -11,7 +11,7 @@
 #include <string>
 #include <vector>
 #include "sf_internal.h"
-#include "sf_kernels.cuh"
+#include "sf_pairs.cuh"
 
 using namespace sf;
 
@@ -20,12 +20,12 @@ namespace
 thread_local std::string g_createError;
 
 enum KernelId {
-    K_BEGIN = 0, K_HASH, K_RADIX_HIST, K_RADIX_SCAN, K_RADIX_SCATTER, K_CLEAR_CELLS, K_CELL_BOUNDS, K_REORDER,
+    K_BEGIN = 0, K_HASH, K_RADIX_HIST, K_RADIX_SCAN, K_RADIX_SCATTER, K_CLEAR_CELLS, K_CELL_BOUNDS, K_BRICK_COMPACT, K_REORDER,
     K_DENSITY, K_CORRECT_DENSITY, K_FORCE, K_VISC_INTEGRATE, K_MARSHAL, K_COUNT
 };
 const char* const kKernelNames[K_COUNT] = {
-    "k_begin_step", "k_hash", "k_radix_hist", "k_radix_scan", "k_radix_scatter", "k_clear_cells", "k_cell_bounds", "k_reorder",
-    "k_density", "k_correct_density", "k_force", "k_visc_integrate", "k_marshal"
+    "k_begin_step", "k_hash", "k_radix_hist", "k_radix_scan", "k_radix_scatter", "k_clear_cells", "k_cell_bounds", "k_brick_compact",
+    "k_reorder", "k_density", "k_correct_density", "k_force", "k_visc_integrate", "k_marshal"
 };
 
 struct PendingEvent {
@@ -58,6 +58,7 @@ struct sf_solver {
     uint32_t     radixBlocks = 0;
     int          sortPasses = 0, sortBits[4] = { 0, 0, 0, 0 };
     int          occDensity = 1, occForce = 1, occVisc = 1;
+    uint32_t     numBricks = 0, brickCap = 0;
 
     // measurement
     bool                      profiling = false;
@@ -149,8 +150,6 @@ struct LaunchScope {
 
 inline uint32_t cdiv(uint64_t a, uint32_t b) { return static_cast<uint32_t>((a + b - 1) / b); }
 
-constexpr int kBlockPair = 256; // CTA size of the three pair-loop kernels
-constexpr size_t kTabSmem = sizeof(float) * (kTab + 4);
 
 void fill_dev_params(sf_solver* s)
 {
@@ -186,6 +185,10 @@ void fill_dev_params(sf_solver* s)
     P.n    = s->n;
     P.npad = s->npad;
     P.kmax = s->kmax;
+    P.nbx  = (s->grid[0] + BX - 1) / BX;
+    P.nby  = (s->grid[1] + BY - 1) / BY;
+    P.nbz  = (s->grid[2] + BZ - 1) / BZ;
+    P.numBricks = s->numBricks;
     for(int w = 0; w < 6; ++w) P.nbnd[w] = P.useBoundary ? static_cast<uint32_t>(s->walls[w].size() / 3) : 0u;
     P.bndStride = s->bndStride;
 }
@@ -209,8 +212,7 @@ int ensure_particle_capacity(sf_solver* s, uint32_t n)
     SF_CUDA(s, dev_alloc(s->B.rho2, npad));
     SF_CUDA(s, dev_alloc(s->B.accel, npad));
     SF_CUDA(s, dev_alloc(s->B.nbrCnt, npad));
-    SF_CUDA(s, dev_alloc(s->B.nbrJ, static_cast<size_t>(npad) * s->kmax));
-    SF_CUDA(s, dev_alloc(s->B.nbrIdx, static_cast<size_t>(npad) * s->kmax));
+    SF_CUDA(s, dev_alloc(s->B.nbrL, static_cast<size_t>(npad) * s->kmax));
     s->radixBlocks = cdiv(npad, RS_TILE);
     SF_CUDA(s, dev_alloc(s->B.radixCounts, static_cast<size_t>(s->radixBlocks) * RS_MAXRADIX));
     SF_CUDA(s, dev_alloc(s->B.radixTotals, RS_MAXRADIX));
@@ -231,6 +233,10 @@ int enqueue_substep(sf_solver* s)
     {
         LaunchScope ls(s, K_BEGIN);
         k_begin_step<<<1, 1, 0, st>>>(B.state, P);
+    }
+    if(n == 0) {
+        SF_CUDA(s, cudaGetLastError());
+        return SF_OK;
     }
     {
         LaunchScope ls(s, K_HASH);
@@ -264,16 +270,20 @@ int enqueue_substep(sf_solver* s)
     }
     {
         LaunchScope ls(s, K_CELL_BOUNDS);
-        k_cell_bounds<<<gridN, 256, 0, st>>>(B.keyB, n, B.cellTab, B.state);
+        k_cell_bounds_bricks<<<gridN, 256, 0, st>>>(B.keyB, n, B.cellTab, B.brickFlag, P, B.state);
+    }
+    {
+        LaunchScope ls(s, K_BRICK_COMPACT);
+        k_brick_compact<<<1, 1024, 0, st>>>(B.brickFlag, B.brickList, s->numBricks, B.state);
     }
     {
         LaunchScope ls(s, K_REORDER);
         k_reorder<<<gridN, 256, 0, st>>>(B.keyB, B.vals[cur], B.cellTab, B.posA, B.velA, B.idA, B.posB, B.velB, B.idB, n, B.state);
     }
-    const uint32_t pairBlocks = cdiv(n, kBlockPair);
+    const uint32_t pairGrid = std::min<uint32_t>(s->numBricks, static_cast<uint32_t>(s->numSMs) * 2u);
     {
         LaunchScope ls(s, K_DENSITY);
-        k_density<kBlockPair><<<std::min<uint32_t>(pairBlocks, s->numSMs * s->occDensity), kBlockPair, kTabSmem, st>>>(B, P);
+        k_density_brick<<<std::min<uint32_t>(pairGrid, s->numSMs * s->occDensity), kBrickThreads, kSmemDensity, st>>>(B, P);
     }
     if(P.correctDensity) {
         LaunchScope ls(s, K_CORRECT_DENSITY);
@@ -282,11 +292,11 @@ int enqueue_substep(sf_solver* s)
     }
     {
         LaunchScope ls(s, K_FORCE);
-        k_force<kBlockPair><<<std::min<uint32_t>(pairBlocks, s->numSMs * s->occForce), kBlockPair, kTabSmem, st>>>(B, P);
+        k_force_brick<<<std::min<uint32_t>(pairGrid, s->numSMs * s->occForce), kBrickThreads, kSmemPair, st>>>(B, P);
     }
     {
         LaunchScope ls(s, K_VISC_INTEGRATE);
-        k_visc_integrate<kBlockPair><<<std::min<uint32_t>(pairBlocks, s->numSMs * s->occVisc), kBlockPair, kTabSmem, st>>>(B, P);
+        k_visc_brick<<<std::min<uint32_t>(pairGrid, s->numSMs * s->occVisc), kBrickThreads, kSmemPair, st>>>(B, P);
     }
     SF_CUDA(s, cudaGetLastError());
     return SF_OK;
@@ -397,12 +407,12 @@ int sf_create(const sf_params* p, int device, sf_solver** out)
     if(e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&s->hostState), sizeof(DevState));
     if(e == cudaSuccess) e = cudaEventCreate(&s->timerA);
     if(e == cudaSuccess) e = cudaEventCreate(&s->timerB);
-    if(e == cudaSuccess) e = cudaFuncSetAttribute(k_density<kBlockPair>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kTabSmem));
-    if(e == cudaSuccess) e = cudaFuncSetAttribute(k_force<kBlockPair>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kTabSmem));
-    if(e == cudaSuccess) e = cudaFuncSetAttribute(k_visc_integrate<kBlockPair>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kTabSmem));
-    if(e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->occDensity, k_density<kBlockPair>, kBlockPair, kTabSmem);
-    if(e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->occForce, k_force<kBlockPair>, kBlockPair, kTabSmem);
-    if(e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->occVisc, k_visc_integrate<kBlockPair>, kBlockPair, kTabSmem);
+    if(e == cudaSuccess) e = cudaFuncSetAttribute(k_density_brick, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemDensity));
+    if(e == cudaSuccess) e = cudaFuncSetAttribute(k_force_brick, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemPair));
+    if(e == cudaSuccess) e = cudaFuncSetAttribute(k_visc_brick, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemPair));
+    if(e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->occDensity, k_density_brick, kBrickThreads, kSmemDensity);
+    if(e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->occForce, k_force_brick, kBrickThreads, kSmemPair);
+    if(e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->occVisc, k_visc_brick, kBrickThreads, kSmemPair);
     if(e != cudaSuccess) {
         const std::string msg = std::string("sf_create: ") + cudaGetErrorString(e);
         sf_destroy(s);
@@ -426,7 +436,7 @@ void sf_destroy(sf_solver* s)
     DevBuffers& B = s->B;
     cudaFree(B.posA); cudaFree(B.velA); cudaFree(B.posB); cudaFree(B.velB); cudaFree(B.idA); cudaFree(B.idB);
     for(int i = 0; i < 2; ++i) { cudaFree(B.keys[i]); cudaFree(B.vals[i]); }
-    cudaFree(B.cellTab); cudaFree(B.rho); cudaFree(B.rho2); cudaFree(B.accel); cudaFree(B.nbrJ); cudaFree(B.nbrIdx); cudaFree(B.nbrCnt);
+    cudaFree(B.cellTab); cudaFree(B.rho); cudaFree(B.rho2); cudaFree(B.accel); cudaFree(B.nbrL); cudaFree(B.nbrCnt); cudaFree(B.brickFlag); cudaFree(B.brickList);
     cudaFree(B.tabW); cudaFree(B.tabG); cudaFree(B.bnd); cudaFree(B.radixCounts); cudaFree(B.radixTotals); cudaFree(B.state);
     cudaFree(s->stage);
     if(s->hostState) cudaFreeHost(s->hostState);
@@ -564,6 +574,16 @@ int sf_make_ready(sf_solver* s)
     if(s->ncells > s->cellCap || !s->B.cellTab) {
         SF_CUDA(s, dev_alloc(s->B.cellTab, s->ncells + 2));
         s->cellCap = s->ncells;
+    }
+    {
+        const uint32_t nb = static_cast<uint32_t>((s->grid[0] + BX - 1) / BX) * ((s->grid[1] + BY - 1) / BY) * ((s->grid[2] + BZ - 1) / BZ);
+        if(nb > s->brickCap || !s->B.brickFlag) {
+            SF_CUDA(s, dev_alloc(s->B.brickFlag, nb + 1));
+            SF_CUDA(s, dev_alloc(s->B.brickList, nb + 1));
+            s->brickCap = nb;
+        }
+        SF_CUDA(s, cudaMemsetAsync(s->B.brickFlag, 0, sizeof(uint32_t) * (nb + 1), s->stream));
+        s->numBricks = nb;
     }
     if(!s->B.tabW) {
         SF_CUDA(s, dev_alloc(s->B.tabW, kTableEntries + 3));
@@ -755,29 +775,40 @@ int sf_grid_dims(sf_solver* s, int32_t n3[3])
 
 static int neighbor_lists_host(sf_solver* s, std::vector<uint32_t>& counts, std::vector<uint32_t>* ids)
 {
-    const uint32_t        n = s->n;
-    std::vector<uint32_t> cnt(n), perm(n);
-    SF_CUDA(s, cudaMemcpy(cnt.data(), s->B.nbrCnt, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));
-    SF_CUDA(s, cudaMemcpy(perm.data(), s->B.idA, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));
+    // neighbour sets of the last substep's binning, by traversal of the device cell tables (CSR in two passes)
+    const uint32_t n = s->n;
     counts.assign(n, 0);
-    uint32_t maxc = 0;
-    for(uint32_t p = 0; p < n; ++p) {
-        counts[perm[p]] = cnt[p] & 16383u;
-        maxc            = std::max(maxc, cnt[p] & 16383u);
+    if(n == 0) {
+        if(ids) ids->clear();
+        return SF_OK;
     }
+    if(!s->B.keyB) return fail(s, SF_ERR_INVALID, "no substep has run yet");
+    uint32_t* dCounts = nullptr;
+    SF_CUDA(s, cudaMalloc(reinterpret_cast<void**>(&dCounts), sizeof(uint32_t) * n));
+    k_neighbor_count<<<cdiv(n, 128), 128, 0, s->stream>>>(s->B, s->P, dCounts);
+    cudaError_t e = cudaMemcpyAsync(counts.data(), dCounts, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, s->stream);
+    if(e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    cudaFree(dCounts);
+    SF_CUDA(s, e);
     if(!ids) return SF_OK;
-    maxc = std::min<uint32_t>(maxc, s->kmax);
-    std::vector<uint32_t> rows(static_cast<size_t>(maxc) * s->npad);
-    if(maxc) SF_CUDA(s, cudaMemcpy(rows.data(), s->B.nbrJ, sizeof(uint32_t) * rows.size(), cudaMemcpyDeviceToHost));
-    std::vector<uint64_t> offset(n + 1, 0);
+    std::vector<unsigned long long> offset(n + 1, 0);
     for(uint32_t i = 0; i < n; ++i) offset[i + 1] = offset[i] + counts[i];
     ids->assign(offset[n], 0);
-    for(uint32_t p = 0; p < n; ++p) {
-        const uint32_t c   = std::min<uint32_t>(cnt[p] & 16383u, maxc);
-        uint32_t*      dst = ids->data() + offset[perm[p]];
-        for(uint32_t k = 0; k < c; ++k) dst[k] = perm[rows[static_cast<size_t>(k) * s->npad + p]];
-        std::sort(dst, dst + c);
+    if(offset[n] == 0) return SF_OK;
+    unsigned long long* dOff = nullptr;
+    uint32_t*           dIds = nullptr;
+    SF_CUDA(s, cudaMalloc(reinterpret_cast<void**>(&dOff), sizeof(unsigned long long) * (n + 1)));
+    e = cudaMalloc(reinterpret_cast<void**>(&dIds), sizeof(uint32_t) * offset[n]);
+    if(e == cudaSuccess) e = cudaMemcpyAsync(dOff, offset.data(), sizeof(unsigned long long) * (n + 1), cudaMemcpyHostToDevice, s->stream);
+    if(e == cudaSuccess) {
+        k_neighbor_fill<<<cdiv(n, 128), 128, 0, s->stream>>>(s->B, s->P, dOff, dIds);
+        e = cudaMemcpyAsync(ids->data(), dIds, sizeof(uint32_t) * offset[n], cudaMemcpyDeviceToHost, s->stream);
     }
+    if(e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    cudaFree(dOff);
+    cudaFree(dIds);
+    SF_CUDA(s, e);
+    for(uint32_t i = 0; i < n; ++i) std::sort(ids->begin() + offset[i], ids->begin() + offset[i + 1]);
     return SF_OK;
 }
 

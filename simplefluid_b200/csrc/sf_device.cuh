@@ -10,12 +10,15 @@
 //   keyB          : cell key per sorted slot ((cz*ny+cy)*nx+cx, reference A.7)
 //   cellTab       : uint2 {begin,end} sorted-slot range per cell, {0,0} when empty
 //   rho           : density per sorted slot
-//   nbrJ/nbrIdx   : neighbour list built once per substep by the density pass and reused by the
+//   brickList     : ids of the non-empty cell bricks (BX x BY x BZ cells) of this substep, in z-major
+//                   order; the three pair kernels are persistent CTAs that pull bricks from it
+//   nbrL          : neighbour list built once per substep by the density pass and reused by the
 //                   force and viscosity passes: ELL layout [k][slot] (row stride npad) so a warp
-//                   reads/writes 128 B rows; nbrJ = neighbour slot (or wall-particle index),
-//                   nbrIdx = kernel-table index min(trunc(sqrt(d2)*invStep), 10000) shared by the
-//                   cubic-W and spiky-grad tables
-//   nbrCnt        : packed counts: fluid (14 bit) | wallX (6) | wallY (6) | wallZ (6)
+//                   reads/writes 128 B rows; entry = brick-local halo index of the neighbour (16 bit,
+//                   or wall-particle index) | kernel-table index min(trunc(sqrt(d2)*invStep), 10000)
+//                   << 16, the index being shared by the cubic-W and spiky-grad tables
+//   nbrCnt        : packed counts: fluid (14 bit) | wallX (6) | wallY (6) | wallZ (6);
+//                   0xffffffff = no list (capacity exceeded): the later passes re-traverse the cells
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -32,6 +35,8 @@ struct DevParams {
     int   useBoundary, attractive, correctDensity, capture;
     uint32_t n, npad;
     int      kmax;
+    int      nbx, nby, nbz; // brick grid
+    uint32_t numBricks;
     uint32_t nbnd[6];     // wall particle counts
     uint32_t bndStride;   // slots per wall in the bnd array
 };
@@ -46,6 +51,9 @@ struct DevState {
     unsigned errFlags;    // SF_DEVERR_*
     unsigned nbrMax;      // largest neighbour count seen (diagnostics)
     unsigned long long stepsDone;
+    unsigned brickCount;  // non-empty bricks of this substep
+    unsigned cursor[4];   // work cursors of the persistent pair kernels (density, force, viscosity)
+    unsigned fallbackBricks, fallbackParticles; // diagnostics: halos that did not fit smem / lists that overflowed
 };
 
 enum : unsigned { SF_DEVERR_NBR_OVERFLOW = 1u, SF_DEVERR_WALL_OVERFLOW = 2u };
@@ -59,9 +67,10 @@ struct DevBuffers {
     float*    rho;
     float*    rho2;       // correctDensity scratch
     float4*   accel;      // capture only
-    uint32_t* nbrJ;
-    uint16_t* nbrIdx;
+    uint32_t* nbrL;
     uint32_t* nbrCnt;
+    uint32_t* brickFlag;
+    uint32_t* brickList;
     float *tabW, *tabG;   // kTableEntries each
     float4*   bnd;        // [6][bndStride]
     uint32_t* radixCounts;

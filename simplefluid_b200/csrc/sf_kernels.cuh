@@ -269,16 +269,6 @@ __global__ void k_clear_cells(uint4* __restrict__ tab, size_t nvec, const DevSta
     for(size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < nvec; i += static_cast<size_t>(gridDim.x) * blockDim.x) tab[i] = z;
 }
 
-__global__ void k_cell_bounds(const uint32_t* __restrict__ keys, uint32_t n, uint2* __restrict__ cellTab, const DevState* st)
-{
-    if(st->skip) return;
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if(p >= n) return;
-    const uint32_t k = keys[p];
-    if(p == 0 || keys[p - 1] != k) cellTab[k].x = p;
-    if(p == n - 1 || keys[p + 1] != k) cellTab[k].y = p + 1;
-}
-
 // Gather A -> B in key order.  The radix sort is stable with respect to the previous substep's
 // order, not the original ids, so inside each cell the slot is re-ranked by original id: that
 // reproduces the ascending-id cell lists of the reference's serial push_back (A.7) and with it the
@@ -304,296 +294,6 @@ __global__ void k_reorder(const uint32_t* __restrict__ keys, const uint32_t* __r
     posB[dst]          = x;
     velB[dst]          = v;
     idB[dst]           = myId;
-}
-
-// ------------------------------------------------------------------------------------------------
-// neighbour traversal shared by the density pass: the 27 cells in reference order collapse to 9
-// contiguous slot runs because the 3 x-adjacent cells of a row are adjacent in key order.
-struct Run {
-    uint32_t b, e;
-};
-__device__ __forceinline__ Run row_run(const uint2* __restrict__ cellTab, int rowBase, int x0, int x1)
-{
-    Run r{ 0xffffffffu, 0u };
-    for(int x = x0; x <= x1; ++x) {
-        const uint2 ce = __ldg(&cellTab[rowBase + x]);
-        if(ce.y > ce.x) {
-            r.b = min(r.b, ce.x);
-            r.e = max(r.e, ce.y);
-        }
-    }
-    if(r.e == 0u) r.b = 0u;
-    return r;
-}
-
-__device__ __forceinline__ void nbr_append(const DevBuffers& B, const DevParams& P, uint32_t p, uint32_t& k, uint32_t j, uint32_t idx)
-{
-    if(k < static_cast<uint32_t>(P.kmax)) {
-        B.nbrJ[static_cast<size_t>(k) * P.npad + p]   = j;
-        B.nbrIdx[static_cast<size_t>(k) * P.npad + p] = static_cast<uint16_t>(idx);
-    }
-    ++k;
-}
-
-// (2) density (A.8) + equation of state, and the neighbour list for the two later passes.
-template<int BLOCK>
-__global__ void __launch_bounds__(BLOCK)
-k_density(DevBuffers B, DevParams P)
-{
-    if(B.state->skip) return;
-    extern __shared__ float s_tab[]; // cubic W table
-    for(int i = threadIdx.x; i <= kTab; i += BLOCK) s_tab[i] = B.tabW[i];
-    __syncthreads();
-
-    for(uint32_t base = blockIdx.x * BLOCK; base < P.n; base += gridDim.x * BLOCK) {
-        const uint32_t p = base + threadIdx.x;
-        if(p >= P.n) continue;
-        const float4   xp  = B.posB[p];
-        const uint32_t key = B.keyB[p];
-        const int      cx  = static_cast<int>(key % static_cast<uint32_t>(P.nx));
-        const int      t   = static_cast<int>(key / static_cast<uint32_t>(P.nx));
-        const int      cy = t % P.ny, cz = t / P.ny;
-        const int      x0 = max(cx - 1, 0), x1 = min(cx + 1, P.nx - 1);
-
-        float    S = P.Wzero;
-        uint32_t k = 0;
-        for(int dz = -1; dz <= 1; ++dz) {
-            const int z = cz + dz;
-            if(z < 0 || z >= P.nz) continue;
-            for(int dy = -1; dy <= 1; ++dy) {
-                const int y = cy + dy;
-                if(y < 0 || y >= P.ny) continue;
-                const Run run = row_run(B.cellTab, (z * P.ny + y) * P.nx, x0, x1);
-                for(uint32_t j = run.b; j < run.e; ++j) {
-                    if(j == p) continue;
-                    const float4 xq = B.posB[j];
-                    const float  d2 = dist2(xq.x - xp.x, xq.y - xp.y, xq.z - xp.z);
-                    if(P.radius2 >= d2) {
-                        const uint32_t idx = table_index(d2, P.invStep);
-                        S += s_tab[idx];
-                        nbr_append(B, P, p, k, j, idx);
-                    }
-                }
-            }
-        }
-        const uint32_t nFluid = k;
-        uint32_t       nWall[3] = { 0, 0, 0 };
-        if(P.useBoundary) {
-#define SF_WALL_DENSITY(A)                                                                               \
-    {                                                                                                    \
-        const int w = wall_of<A>(P, xp);                                                                 \
-        if(w >= 0) {                                                                                     \
-            const float3   xs = wall_shift<A>(P, xp);                                                    \
-            const float4*  bw = B.bnd + static_cast<size_t>(w) * P.bndStride;                            \
-            const uint32_t nb = P.nbnd[w];                                                               \
-            const uint32_t k0 = k;                                                                       \
-            for(uint32_t b = 0; b < nb; ++b) {                                                           \
-                const float4 xb = __ldg(&bw[b]);                                                         \
-                const float  d2 = dist2(xb.x - xs.x, xb.y - xs.y, xb.z - xs.z);                          \
-                if(P.radius2 >= d2) {                                                                    \
-                    const uint32_t idx = table_index(d2, P.invStep);                                     \
-                    S += s_tab[idx];                                                                     \
-                    nbr_append(B, P, p, k, b, idx);                                                      \
-                }                                                                                        \
-            }                                                                                            \
-            nWall[A] = k - k0;                                                                           \
-        }                                                                                                \
-    }
-            SF_WALL_DENSITY(0)
-            SF_WALL_DENSITY(1)
-            SF_WALL_DENSITY(2)
-#undef SF_WALL_DENSITY
-        }
-        unsigned err = 0;
-        if(k > static_cast<uint32_t>(P.kmax) || nFluid > 16383u) err |= SF_DEVERR_NBR_OVERFLOW;
-        if(nWall[0] > 63u || nWall[1] > 63u || nWall[2] > 63u) err |= SF_DEVERR_WALL_OVERFLOW;
-        if(err) atomicOr(&B.state->errFlags, err);
-        B.nbrCnt[p] = nFluid | (nWall[0] << 14) | (nWall[1] << 20) | (nWall[2] << 26);
-
-        const float rho = (1.0f > S) ? 0.0f : fminf(fmaxf(S * P.mass, P.rhoMin), P.rhoMax);
-        B.rho[p]        = rho;
-        if(!P.correctDensity) {
-            // pair-loop terms of A.11 / A.13 hoisted per particle: identical values, computed once
-            float pterm, inv;
-            if(1e-8 > static_cast<double>(rho)) {
-                pterm = __int_as_float(0x7fc00000); // NaN marks "rho < 1e-8: skipped as a neighbour"
-                inv   = 1.0f / rho;
-            } else {
-                pterm = pressure_of(P, rho) / (rho * rho);
-                inv   = 1.0f / rho;
-            }
-            B.posB[p].w = pterm;
-            B.velB[p].w = inv;
-        }
-    }
-}
-
-// correctDensity (A.9, default off): Shepard normalisation over the neighbour list, then the
-// per-particle terms from the corrected density.
-__global__ void k_correct_density(DevBuffers B, DevParams P)
-{
-    if(B.state->skip) return;
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if(p >= P.n) return;
-    const float    rp  = B.rho[p];
-    const uint32_t cnt = B.nbrCnt[p];
-    const uint32_t nF = cnt & 16383u, nW = ((cnt >> 14) & 63u) + ((cnt >> 20) & 63u) + ((cnt >> 26) & 63u);
-    float          T = P.Wzero / rp;
-    for(uint32_t k = 0; k < nF; ++k) {
-        const uint32_t j  = B.nbrJ[static_cast<size_t>(k) * P.npad + p];
-        const float    rq = B.rho[j];
-        if(!(static_cast<double>(rq) >= 1e-8)) continue;
-        T += __ldg(&B.tabW[B.nbrIdx[static_cast<size_t>(k) * P.npad + p]]) / rq;
-    }
-    for(uint32_t k = nF; k < nF + nW; ++k) T += __ldg(&B.tabW[B.nbrIdx[static_cast<size_t>(k) * P.npad + p]]) / P.rho0;
-    B.rho2[p] = (static_cast<double>(T) > 1e-8) ? rp / fminf(T * P.mass, P.rhoMax) : 0.0f;
-}
-
-__global__ void k_density_terms(DevBuffers B, DevParams P)
-{
-    if(B.state->skip) return;
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if(p >= P.n) return;
-    const float rho = B.rho2[p];
-    B.rho[p]        = rho;
-    B.posB[p].w     = (1e-8 > static_cast<double>(rho)) ? __int_as_float(0x7fc00000) : pressure_of(P, rho) / (rho * rho);
-    B.velB[p].w     = 1.0f / rho;
-}
-
-// ------------------------------------------------------------------------------------------------
-// (3a) pressure acceleration (A.11) + gravity (A.10) + velocity update (A.12), over the list
-template<int BLOCK>
-__global__ void __launch_bounds__(BLOCK)
-k_force(DevBuffers B, DevParams P)
-{
-    if(B.state->skip) return;
-    extern __shared__ float s_tab[]; // spiky gradW/r table
-    for(int i = threadIdx.x; i <= kTab; i += BLOCK) s_tab[i] = B.tabG[i];
-    __syncthreads();
-    const float dt = B.state->dt;
-
-    for(uint32_t base = blockIdx.x * BLOCK; base < P.n; base += gridDim.x * BLOCK) {
-        const uint32_t p = base + threadIdx.x;
-        if(p >= P.n) continue;
-        const float4 xp = B.posB[p]; // w = P_p / rho_p^2
-        float4       vp = B.velB[p]; // w = 1 / rho_p
-        const float  rp = B.rho[p];
-        float        ax = 0.f, ay = 0.f, az = 0.f;
-        if(!(1e-8 > static_cast<double>(rp))) {
-            const uint32_t cnt = B.nbrCnt[p];
-            const uint32_t nF  = min(cnt & 16383u, static_cast<uint32_t>(P.kmax));
-            for(uint32_t k = 0; k < nF; ++k) {
-                const uint32_t j   = B.nbrJ[static_cast<size_t>(k) * P.npad + p];
-                const uint32_t idx = B.nbrIdx[static_cast<size_t>(k) * P.npad + p];
-                const float4   xq  = B.posB[j];
-                if(xq.w != xq.w) continue; // rho_q < 1e-8
-                const float dx = xq.x - xp.x, dy = xq.y - xp.y, dz = xq.z - xp.z;
-                const float g  = s_tab[idx];
-                const float fp = xq.w + xp.w;
-                ax += fp * (g * dx);
-                ay += fp * (dy * g);
-                az += fp * (g * dz);
-            }
-            if(P.useBoundary) {
-                uint32_t k = nF;
-#define SF_WALL_FORCE(A, SH)                                                                              \
-    {                                                                                                    \
-        const uint32_t nw = (cnt >> SH) & 63u;                                                           \
-        if(nw) {                                                                                         \
-            const int     w  = wall_of<A>(P, xp);                                                        \
-            const float3  xs = wall_shift<A>(P, xp);                                                     \
-            const float4* bw = B.bnd + static_cast<size_t>(w) * P.bndStride;                             \
-            for(uint32_t e = 0; e < nw && k < static_cast<uint32_t>(P.kmax); ++e, ++k) {                 \
-                const uint32_t b   = B.nbrJ[static_cast<size_t>(k) * P.npad + p];                        \
-                const uint32_t idx = B.nbrIdx[static_cast<size_t>(k) * P.npad + p];                      \
-                const float4   xb  = __ldg(&bw[b]);                                                      \
-                const float    dx = xb.x - xs.x, dy = xb.y - xs.y, dz = xb.z - xs.z;                     \
-                const float    g = s_tab[idx];                                                           \
-                ax += xp.w * (g * dx);                                                                   \
-                ay += xp.w * (dy * g);                                                                   \
-                az += xp.w * (g * dz);                                                                   \
-            }                                                                                            \
-        }                                                                                                \
-    }
-                SF_WALL_FORCE(0, 14)
-                SF_WALL_FORCE(1, 20)
-                SF_WALL_FORCE(2, 26)
-#undef SF_WALL_FORCE
-            }
-            ax = (ax * P.mass) * P.stiffness;
-            ay = (ay * P.mass) * P.stiffness;
-            az = (az * P.mass) * P.stiffness;
-        }
-        if(P.capture) B.accel[p] = make_float4(ax, ay, az, 0.f);
-        // addGravity (A.10) then updateVelocity (A.12)
-        vp.y = static_cast<float>(static_cast<double>(vp.y) - static_cast<double>(dt) * 9.8);
-        vp.x = dt * ax + vp.x;
-        vp.y = dt * ay + vp.y;
-        vp.z = dt * az + vp.z;
-        B.velB[p] = vp; // w still 1/rho_p: the viscosity pass reads {v*, 1/rho} of its neighbours in one load
-    }
-}
-
-// (3b) XSPH viscosity (A.13) + updatePosition with wall clamp/restitution (A.14) + max |v|^2 for
-// the next substep's computeTimeStep (A.5).  Writes the new state into A (sorted order of B).
-template<int BLOCK>
-__global__ void __launch_bounds__(BLOCK)
-k_visc_integrate(DevBuffers B, DevParams P)
-{
-    if(B.state->skip) return;
-    extern __shared__ float s_tab[]; // cubic W table
-    __shared__ float        s_max[BLOCK / 32];
-    for(int i = threadIdx.x; i <= kTab; i += BLOCK) s_tab[i] = B.tabW[i];
-    __syncthreads();
-    const float dt   = B.state->dt;
-    float       vmax = FLT_MIN;
-
-    for(uint32_t base = blockIdx.x * BLOCK; base < P.n; base += gridDim.x * BLOCK) {
-        const uint32_t p = base + threadIdx.x;
-        if(p >= P.n) continue;
-        const float4   xp  = B.posB[p];
-        const float4   vp  = B.velB[p];
-        const uint32_t cnt = B.nbrCnt[p];
-        const uint32_t nF  = min(cnt & 16383u, static_cast<uint32_t>(P.kmax));
-        float          sx = 0.f, sy = 0.f, sz = 0.f;
-        for(uint32_t k = 0; k < nF; ++k) {
-            const uint32_t j   = B.nbrJ[static_cast<size_t>(k) * P.npad + p];
-            const uint32_t idx = B.nbrIdx[static_cast<size_t>(k) * P.npad + p];
-            const float4   vq  = B.velB[j]; // {v*, 1/rho_q}
-            const float    w   = s_tab[idx];
-            const float    dvx = vq.x - vp.x, dvy = vq.y - vp.y, dvz = vq.z - vp.z;
-            sx += (vq.w * dvx) * w;
-            sy += (dvy * vq.w) * w;
-            sz += (dvz * vq.w) * w;
-        }
-        float v[3] = { P.viscosity * (sx * P.mass) + vp.x, P.viscosity * (sy * P.mass) + vp.y, P.viscosity * (sz * P.mass) + vp.z };
-        float x[3] = { xp.x, xp.y, xp.z };
-#pragma unroll
-        for(int d = 0; d < 3; ++d) {
-            const float lo = P.bmin[d] + P.r, hi = P.bmax[d] - P.r;
-            float       xn = v[d] * dt + x[d];
-            if(lo > xn) {
-                xn   = lo;
-                v[d] = -(v[d] * P.restitution);
-            } else if(xn > hi) {
-                xn   = hi;
-                v[d] = -(v[d] * P.restitution);
-            }
-            x[d] = xn;
-        }
-        B.posA[p] = make_float4(x[0], x[1], x[2], 0.f);
-        B.velA[p] = make_float4(v[0], v[1], v[2], 0.f);
-        B.idA[p]  = B.idB[p]; // A now holds this substep's sorted order
-        vmax      = fmaxf(vmax, (v[1] * v[1] + v[0] * v[0]) + v[2] * v[2]);
-    }
-    for(int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-    if((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = vmax;
-    __syncthreads();
-    if(threadIdx.x < 32) {
-        float m = threadIdx.x < BLOCK / 32 ? s_max[threadIdx.x] : FLT_MIN;
-        for(int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        if(threadIdx.x == 0) atomicMax(&B.state->maxv2Bits[B.state->step & 1u], __float_as_uint(m));
-    }
 }
 
 // ------------------------------------------------------------------------------------------------
