@@ -21,9 +21,9 @@ __device__ __forceinline__ float dist2(float dx, float dy, float dz) { return (d
 // A.2: tab[min((uint32)(int64)(sqrtf(d2) * invStep), 10000)]
 __device__ __forceinline__ uint32_t table_index(float d2, float invStep)
 {
-    const float    t = sqrtf(d2) * invStep;
-    const uint32_t i = static_cast<uint32_t>(__float2ll_rz(t));
-    return i > static_cast<uint32_t>(kTab) ? static_cast<uint32_t>(kTab) : i;
+    // t >= 0 and far below 2^32, so the reference's (uint32)(int64) truncation equals a direct u32 truncation
+    const float t = sqrtf(d2) * invStep;
+    return min(__float2uint_rz(t), static_cast<uint32_t>(kTab));
 }
 
 // A.11 Pr(rho)
