@@ -56,7 +56,7 @@ def library_path():
 
 def build_library(force=False, verbose=False):
     """Compile libsf_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
-    args = ["make", "-C", _CSRC, "--no-print-directory"]
+    args = ["make", "-C", _CSRC, "--no-print-directory", "all"]
     if force:
         args.append("-B")
     r = subprocess.run(args, capture_output=True, text=True)

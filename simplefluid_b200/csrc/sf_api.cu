@@ -630,10 +630,8 @@ int sf_advance_frame(sf_solver* s, float* dt_out)
     int rc = require_ready(s);
     if(rc) return rc;
     SF_CUDA(s, cudaSetDevice(s->device));
-    if(s->n) {
-        rc = enqueue_substep(s);
-        if(rc) return rc;
-    }
+    rc = enqueue_substep(s);
+    if(rc) return rc;
     rc = read_state(s);
     if(rc) return rc;
     if(dt_out) *dt_out = s->hostState->dt;
@@ -651,7 +649,7 @@ int sf_advance_steps(sf_solver* s, uint32_t nsteps, float* time_out)
         if(rc) return rc;
         t0 = s->hostState->frameTime;
     }
-    for(uint32_t i = 0; i < nsteps && s->n; ++i) {
+    for(uint32_t i = 0; i < nsteps; ++i) {
         rc = enqueue_substep(s);
         if(rc) return rc;
     }
@@ -679,7 +677,7 @@ int sf_advance_frame_time(sf_solver* s, double frame_time, float* time_out, uint
     patch.skip        = 0;
     SF_CUDA(s, cudaMemcpyAsync(s->B.state, &patch, sizeof(patch), cudaMemcpyHostToDevice, s->stream));
     const double dtMax = static_cast<double>(s->P.dtMax);
-    for(int guard = 0; guard < 100000 && s->n; ++guard) {
+    for(int guard = 0; guard < 100000; ++guard) {
         rc = read_state(s);
         if(rc) return rc;
         const double remaining = frame_time - static_cast<double>(s->hostState->frameTime);
