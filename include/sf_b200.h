@@ -163,6 +163,12 @@ int sf_upload_particles_global(sf_solver* s, const float* pos_xyz, const float* 
 int sf_slab_info(sf_solver* s, int32_t* z_begin, int32_t* z_end, uint32_t* n_owned, uint32_t* n_ghost);
 /* Owned particles with their global (original) ids. */
 int sf_download_owned(sf_solver* s, uint32_t* ids, float* pos_xyz, float* vel_xyz, uint32_t cap, uint32_t* n_out);
+/* Host-side pieces of the decomposition (no GPU needed): count-balanced cut planes (cuts[nranks+1]) from a
+ * per-layer particle histogram; the one-layer-per-substep rebalancing rule applied to the all-gathered table
+ * (8 uint32 per rank: sendLo, sendHi, nOwn, firstLayerCount, lastLayerCount, ...); global cell layer per particle. */
+int sf_slab_plan(const uint64_t* layer_counts, int32_t nz, int32_t nranks, int32_t* cuts);
+int sf_slab_rebalance(const uint32_t* table, int32_t nranks, int32_t nz, int32_t* cuts);
+int sf_cell_layers(const sf_params* p, const float* pos_xyz, uint32_t n, int32_t* layers);
 
 #ifdef __cplusplus
 }

@@ -25,6 +25,7 @@ EXPORTS = [
     "sf_synchronize", "sf_step_host", "sf_set_capture", "sf_field_size", "sf_download_field", "sf_grid_dims",
     "sf_profile_enable", "sf_profile_reset", "sf_profile_get", "sf_launch_count", "sf_timer_start", "sf_timer_stop",
     "sf_comm_unique_id", "sf_comm_init", "sf_upload_particles_global", "sf_slab_info", "sf_download_owned",
+    "sf_slab_plan", "sf_slab_rebalance", "sf_cell_layers",
 ]
 
 
@@ -101,6 +102,7 @@ def library():
         "sf_upload_particles_global": [vp, vp, vp, u32],
         "sf_slab_info": [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(u32), C.POINTER(u32)],
         "sf_download_owned": [vp, vp, vp, vp, u32, C.POINTER(u32)],
+        "sf_slab_plan": [vp, i32, i32, vp], "sf_slab_rebalance": [vp, i32, i32, vp], "sf_cell_layers": [PP, vp, u32, vp],
     }
     for name, argtypes in sig.items():
         fn = getattr(L, name)
@@ -150,6 +152,40 @@ def boundary_generate(params, seed, wall):
     library().sf_boundary_generate(C.byref(params), seed, wall, None, 0, C.byref(n))
     out = np.empty((n.value, 3), np.float32)
     library().sf_boundary_generate(C.byref(params), seed, wall, out.ctypes.data, n.value, C.byref(n))
+    return out
+
+
+def comm_unique_id():
+    """128-byte ncclUniqueId (rank 0 creates it, the caller distributes it to the other ranks)."""
+    buf = C.create_string_buffer(128)
+    rc = library().sf_comm_unique_id(buf)
+    if rc:
+        raise SFError(rc, (library().sf_last_error(None) or b"").decode())
+    return buf.raw
+
+
+def slab_plan(layer_counts, nranks):
+    lc = np.ascontiguousarray(layer_counts, np.uint64)
+    cuts = np.zeros(nranks + 1, np.int32)
+    rc = library().sf_slab_plan(lc.ctypes.data, len(lc), nranks, cuts.ctypes.data)
+    if rc:
+        raise SFError(rc, "sf_slab_plan: invalid arguments (too few layers for this many slabs?)")
+    return cuts
+
+
+def slab_rebalance(table, nz, cuts):
+    t = np.ascontiguousarray(table, np.uint32)
+    c = np.ascontiguousarray(cuts, np.int32).copy()
+    rc = library().sf_slab_rebalance(t.ctypes.data, len(c) - 1, nz, c.ctypes.data)
+    if rc:
+        raise SFError(rc, "sf_slab_rebalance: invalid arguments")
+    return c
+
+
+def cell_layers(params, pos):
+    pos = np.ascontiguousarray(pos, np.float32)
+    out = np.empty(len(pos), np.int32)
+    library().sf_cell_layers(C.byref(params), pos.ctypes.data, len(pos), out.ctypes.data)
     return out
 
 
@@ -306,6 +342,30 @@ class SPHSolver:
 
     def neighbors(self):
         return self.field(FIELD_NEIGHBOR_COUNT), self.field(FIELD_NEIGHBOR_IDS)
+
+    # -- multi-GPU (z-slabs; one SPHSolver per rank / GPU)
+    def commInit(self, rank, nranks, unique_id_bytes):
+        buf = C.create_string_buffer(bytes(unique_id_bytes), 128)
+        self._ck(self.L.sf_comm_init(self.h, rank, nranks, buf))
+
+    def setParticlesGlobal(self, pos, vel=None):
+        pos = np.ascontiguousarray(pos, np.float32)
+        vel = None if vel is None else np.ascontiguousarray(vel, np.float32)
+        self._ck(self.L.sf_upload_particles_global(self.h, _ptr(pos), _ptr(vel), pos.shape[0]))
+
+    def slabInfo(self):
+        zb, ze, no, ng = C.c_int32(0), C.c_int32(0), C.c_uint32(0), C.c_uint32(0)
+        self._ck(self.L.sf_slab_info(self.h, C.byref(zb), C.byref(ze), C.byref(no), C.byref(ng)))
+        return zb.value, ze.value, no.value, ng.value
+
+    def downloadOwned(self):
+        n = C.c_uint32(0)
+        self._ck(self.L.sf_download_owned(self.h, None, None, None, 0, C.byref(n)))
+        ids = np.empty(n.value, np.uint32)
+        x = np.empty((n.value, 3), np.float32)
+        v = np.empty((n.value, 3), np.float32)
+        self._ck(self.L.sf_download_owned(self.h, ids.ctypes.data, x.ctypes.data, v.ctypes.data, n.value, C.byref(n)))
+        return ids, x, v
 
     # -- measurement
     def profileEnable(self, on=True):

@@ -12,6 +12,7 @@
 #include <vector>
 #include "sf_internal.h"
 #include "sf_pairs.cuh"
+#include "sf_slab.cuh"
 
 using namespace sf;
 
@@ -59,6 +60,25 @@ struct sf_solver {
     int          sortPasses = 0, sortBits[4] = { 0, 0, 0, 0 };
     int          occDensity = 1, occForce = 1, occVisc = 1;
     uint32_t     numBricks = 0, brickCap = 0;
+    uint32_t     nSlots = 0; // live + dead slots of the A arrays (== n on a single GPU)
+
+    // z-slab decomposition (sf_comm_init)
+    struct Slab {
+        bool                 on = false;
+        int                  rank = 0, nranks = 1;
+        ncclComm_t           comm = nullptr;
+        std::vector<int32_t> cur, next; // cut planes (nranks + 1): bounds of this substep / of the next one
+        cudaStream_t         commStream = nullptr;
+        cudaEvent_t          evEdge = nullptr, evExchanged = nullptr;
+        float4 *             sendLo = nullptr, *sendHi = nullptr, *recvLo = nullptr, *recvHi = nullptr;
+        uint32_t             xcap = 0;
+        uint32_t *           layerStart = nullptr, *counters = nullptr, *row = nullptr, *table = nullptr;
+        uint32_t*            hostTable = nullptr; // pinned
+        uint64_t             nGlobal = 0;
+        uint32_t             nOwn = 0;
+        uint64_t             ncellsMax = 0;
+        uint64_t             exchangedParticles = 0;
+    } slab;
 
     // measurement
     bool                      profiling = false;
@@ -189,6 +209,12 @@ void fill_dev_params(sf_solver* s)
     P.nby  = (s->grid[1] + BY - 1) / BY;
     P.nbz  = (s->grid[2] + BZ - 1) / BZ;
     P.numBricks = s->numBricks;
+    P.z0 = 0;
+    P.nzGlobal = s->grid[2];
+    P.zDensLo = P.zForceLo = P.zOwnLo = 0;
+    P.zDensHi = P.zForceHi = P.zOwnHi = s->grid[2];
+    P.zEdge = 0;
+    P.slab  = 0;
     for(int w = 0; w < 6; ++w) P.nbnd[w] = P.useBoundary ? static_cast<uint32_t>(s->walls[w].size() / 3) : 0u;
     P.bndStride = s->bndStride;
 }
@@ -223,44 +249,58 @@ int ensure_particle_capacity(sf_solver* s, uint32_t n)
     return SF_OK;
 }
 
+int slab_exchange(sf_solver* s, uint32_t n, uint32_t nSlots);
+
+// One reference substep (advanceFrame, EXE@0x140016810) as a launch sequence on the solver's stream.
+// n = live particles, nSlots >= n = slots of the A arrays to sort (slab mode keeps last step's dead ghost slots).
 int enqueue_substep(sf_solver* s)
 {
     DevBuffers&     B  = s->B;
     const DevParams P  = s->P;
     cudaStream_t    st = s->stream;
-    const uint32_t  n  = s->n;
-    const uint32_t  gridN = cdiv(n, 256);
+    const bool      slab   = s->slab.on;
+    const uint32_t  n      = s->n;
+    const uint32_t  nSlots = slab ? s->nSlots : n;
+    const uint32_t  gridN  = cdiv(n, 256);
+    if(slab) { // global dt: max |v|^2 over all slabs (uint32 order == float order for non-negative floats)
+        NcclApi& nc = nccl_api();
+        if(nc.AllReduce(B.state->maxv2Bits, B.state->maxv2Bits, 2, ncclUint32, ncclMax, s->slab.comm, st) != ncclSuccess)
+            return fail(s, SF_ERR_COMM, "ncclAllReduce(max |v|^2) failed");
+    }
     {
         LaunchScope ls(s, K_BEGIN);
         k_begin_step<<<1, 1, 0, st>>>(B.state, P);
     }
-    if(n == 0) {
+    if(nSlots == 0 && !slab) {
         SF_CUDA(s, cudaGetLastError());
         return SF_OK;
     }
-    {
-        LaunchScope ls(s, K_HASH);
-        k_hash<<<gridN, 256, 0, st>>>(B.posA, B.keys[0], B.vals[0], P, B.state);
-    }
-    const uint32_t nb = cdiv(n, RS_TILE);
-    int            cur = 0, shift = 0;
-    for(int pass = 0; pass < s->sortPasses; ++pass) {
-        const int radix = 1 << s->sortBits[pass];
+    int cur = 0;
+    if(nSlots) {
         {
-            LaunchScope ls(s, K_RADIX_HIST);
-            k_radix_hist<<<nb, RS_THREADS, 0, st>>>(B.keys[cur], n, shift, radix, B.radixCounts, nb, B.state);
+            LaunchScope ls(s, K_HASH);
+            k_hash<<<cdiv(nSlots, 256), 256, 0, st>>>(B.posA, B.idA, B.keys[0], B.vals[0], nSlots, P, B.state);
         }
-        {
-            LaunchScope ls(s, K_RADIX_SCAN);
-            k_radix_scan<<<radix, 1024, 0, st>>>(B.radixCounts, nb, B.radixTotals, B.state);
+        const uint32_t nb    = cdiv(nSlots, RS_TILE);
+        int            shift = 0;
+        for(int pass = 0; pass < s->sortPasses; ++pass) {
+            const int radix = 1 << s->sortBits[pass];
+            {
+                LaunchScope ls(s, K_RADIX_HIST);
+                k_radix_hist<<<nb, RS_THREADS, 0, st>>>(B.keys[cur], nSlots, shift, radix, B.radixCounts, nb, B.state);
+            }
+            {
+                LaunchScope ls(s, K_RADIX_SCAN);
+                k_radix_scan<<<radix, 1024, 0, st>>>(B.radixCounts, nb, B.radixTotals, B.state);
+            }
+            {
+                LaunchScope ls(s, K_RADIX_SCATTER);
+                k_radix_scatter<<<nb, RS_THREADS, 0, st>>>(B.keys[cur], B.vals[cur], B.keys[cur ^ 1], B.vals[cur ^ 1], nSlots, shift, radix,
+                                                            B.radixCounts, nb, B.radixTotals, B.state);
+            }
+            shift += s->sortBits[pass];
+            cur ^= 1;
         }
-        {
-            LaunchScope ls(s, K_RADIX_SCATTER);
-            k_radix_scatter<<<nb, RS_THREADS, 0, st>>>(B.keys[cur], B.vals[cur], B.keys[cur ^ 1], B.vals[cur ^ 1], n, shift, radix,
-                                                        B.radixCounts, nb, B.radixTotals, B.state);
-        }
-        shift += s->sortBits[pass];
-        cur ^= 1;
     }
     B.keyB = B.keys[cur];
     {
@@ -268,7 +308,7 @@ int enqueue_substep(sf_solver* s)
         const size_t nvec = (s->ncells * sizeof(uint2) + 15) / 16;
         k_clear_cells<<<std::min<uint32_t>(cdiv(nvec, 256), s->numSMs * 16), 256, 0, st>>>(reinterpret_cast<uint4*>(B.cellTab), nvec, B.state);
     }
-    {
+    if(n) {
         LaunchScope ls(s, K_CELL_BOUNDS);
         k_cell_bounds_bricks<<<gridN, 256, 0, st>>>(B.keyB, n, B.cellTab, B.brickFlag, P, B.state);
     }
@@ -276,30 +316,34 @@ int enqueue_substep(sf_solver* s)
         LaunchScope ls(s, K_BRICK_COMPACT);
         k_brick_compact<<<1, 1024, 0, st>>>(B.brickFlag, B.brickList, s->numBricks, B.state);
     }
-    {
-        LaunchScope ls(s, K_REORDER);
-        k_reorder<<<gridN, 256, 0, st>>>(B.keyB, B.vals[cur], B.cellTab, B.posA, B.velA, B.idA, B.posB, B.velB, B.idB, n, B.state);
+    if(slab) k_layer_start<<<cdiv(static_cast<uint32_t>(P.nz) + 1u, 128), 128, 0, st>>>(B.keyB, n, P, s->slab.layerStart);
+    const uint32_t pairGrid = std::max<uint32_t>(1u, std::min<uint32_t>(s->numBricks, static_cast<uint32_t>(s->numSMs) * 2u));
+    if(n) {
+        {
+            LaunchScope ls(s, K_REORDER);
+            k_reorder<<<gridN, 256, 0, st>>>(B.keyB, B.vals[cur], B.cellTab, B.posA, B.velA, B.idA, B.posB, B.velB, B.idB, n, B.state);
+        }
+        {
+            LaunchScope ls(s, K_DENSITY);
+            k_density_brick<<<std::min<uint32_t>(pairGrid, s->numSMs * s->occDensity), kBrickThreads, kSmemDensity, st>>>(B, P);
+        }
+        if(P.correctDensity) {
+            LaunchScope ls(s, K_CORRECT_DENSITY);
+            k_correct_density<<<gridN, 256, 0, st>>>(B, P);
+            k_density_terms<<<gridN, 256, 0, st>>>(B, P);
+        }
+        {
+            LaunchScope ls(s, K_FORCE);
+            k_force_brick<<<std::min<uint32_t>(pairGrid, s->numSMs * s->occForce), kBrickThreads, kSmemPair, st>>>(B, P);
+        }
     }
-    const uint32_t pairGrid = std::min<uint32_t>(s->numBricks, static_cast<uint32_t>(s->numSMs) * 2u);
-    {
-        LaunchScope ls(s, K_DENSITY);
-        k_density_brick<<<std::min<uint32_t>(pairGrid, s->numSMs * s->occDensity), kBrickThreads, kSmemDensity, st>>>(B, P);
-    }
-    if(P.correctDensity) {
-        LaunchScope ls(s, K_CORRECT_DENSITY);
-        k_correct_density<<<gridN, 256, 0, st>>>(B, P);
-        k_density_terms<<<gridN, 256, 0, st>>>(B, P);
-    }
-    {
-        LaunchScope ls(s, K_FORCE);
-        k_force_brick<<<std::min<uint32_t>(pairGrid, s->numSMs * s->occForce), kBrickThreads, kSmemPair, st>>>(B, P);
-    }
-    {
+    if(!slab) {
         LaunchScope ls(s, K_VISC_INTEGRATE);
-        k_visc_brick<<<std::min<uint32_t>(pairGrid, s->numSMs * s->occVisc), kBrickThreads, kSmemPair, st>>>(B, P);
+        k_visc_brick<<<std::min<uint32_t>(pairGrid, s->numSMs * s->occVisc), kBrickThreads, kSmemPair, st>>>(B, P, 0);
+        SF_CUDA(s, cudaGetLastError());
+        return SF_OK;
     }
-    SF_CUDA(s, cudaGetLastError());
-    return SF_OK;
+    return slab_exchange(s, n, nSlots);
 }
 
 int read_state(sf_solver* s)
@@ -323,6 +367,109 @@ int require_ready(sf_solver* s)
     if(!s->ready) return fail(s, SF_ERR_INVALID, "sf_make_ready has not been called");
     return SF_OK;
 }
+} // namespace
+
+namespace
+{
+// P / sort plan / brick grid for the current cut planes: local window = own layers + kGhost on each side
+int slab_configure_window(sf_solver* s)
+{
+    sf_solver::Slab& L = s->slab;
+    const int zb = L.cur[L.rank], ze = L.cur[L.rank + 1];
+    const int nzL = ze - zb + 2 * kGhost;
+    s->ncells    = static_cast<uint64_t>(s->grid[0]) * s->grid[1] * nzL;
+    s->numBricks = static_cast<uint32_t>((s->grid[0] + BX - 1) / BX) * ((s->grid[1] + BY - 1) / BY) * ((nzL + BZ - 1) / BZ);
+    fill_dev_params(s);
+    DevParams& P = s->P;
+    P.nz        = nzL;
+    P.nbz       = (nzL + BZ - 1) / BZ;
+    P.numBricks = s->numBricks;
+    P.z0        = zb - kGhost;
+    P.nzGlobal  = s->grid[2];
+    P.zDensLo = 1;
+    P.zDensHi = nzL - 1;
+    P.zForceLo = 2;
+    P.zForceHi = nzL - 2;
+    P.zOwnLo = kGhost;
+    P.zOwnHi = nzL - kGhost;
+    P.zEdge  = kEdge;
+    P.slab   = 1;
+    int bits = 1;
+    while((1ull << bits) <= s->ncells) ++bits;
+    s->sortPasses = (bits + 7) / 8;
+    for(int i = 0, left = bits; i < s->sortPasses; ++i) {
+        s->sortBits[i] = (left + (s->sortPasses - i) - 1) / (s->sortPasses - i);
+        left -= s->sortBits[i];
+    }
+    return SF_OK;
+}
+
+// Tail of a slab substep: integrate edge bricks, exchange them while the interior bricks integrate.
+int slab_exchange(sf_solver* s, uint32_t n, uint32_t nSlots)
+{
+    sf_solver::Slab& L  = s->slab;
+    DevBuffers&      B  = s->B;
+    const DevParams  P  = s->P;
+    cudaStream_t     cs = s->stream, ms = L.commStream;
+    NcclApi&         nc = nccl_api();
+    const uint32_t   extent = std::max(n, nSlots);
+    const uint32_t   pairGrid = std::max<uint32_t>(1u, std::min<uint32_t>(s->numBricks, static_cast<uint32_t>(s->numSMs) * 2u));
+    if(extent) k_fill_u32<<<std::min<uint32_t>(cdiv(extent, 256), s->numSMs * 8), 256, 0, cs>>>(B.idA, extent, kInvalidId);
+    if(n) {
+        LaunchScope ls(s, K_VISC_INTEGRATE);
+        k_visc_brick<<<std::min<uint32_t>(pairGrid, s->numSMs * s->occVisc), kBrickThreads, kSmemPair, cs>>>(B, P, 1);
+    }
+    SF_CUDA(s, cudaEventRecord(L.evEdge, cs));
+    if(n) { // interior bricks: leave a few CTA slots free so that the pack / NCCL kernels can run beside them
+        LaunchScope    ls(s, K_VISC_INTEGRATE);
+        const uint32_t g = std::min<uint32_t>(pairGrid, s->numSMs * s->occVisc);
+        k_visc_brick<<<g > 32 ? g - 16 : g, kBrickThreads, kSmemPair, cs>>>(B, P, 2);
+    }
+    // ---- communication stream
+    const int hasLower = L.rank > 0, hasUpper = L.rank < L.nranks - 1;
+    SF_CUDA(s, cudaStreamWaitEvent(ms, L.evEdge, 0));
+    SF_CUDA(s, cudaMemsetAsync(L.counters, 0, 2 * sizeof(uint32_t), ms));
+    if(n) k_slab_pack<<<std::min<uint32_t>(cdiv(n, 256), 64), 256, 0, ms>>>(B.posA, B.velA, B.idA, L.layerStart, P, L.next[L.rank], L.next[L.rank + 1],
+                                                                               hasLower, hasUpper, L.sendLo, L.sendHi, L.xcap, L.counters);
+    k_slab_row<<<1, 1, 0, ms>>>(L.layerStart, L.counters, P, L.row);
+    if(nc.AllGather(L.row, L.table, kRowWords, ncclUint32, L.comm, ms) != ncclSuccess) return fail(s, SF_ERR_COMM, "ncclAllGather failed");
+    SF_CUDA(s, cudaMemcpyAsync(L.hostTable, L.table, sizeof(uint32_t) * kRowWords * L.nranks, cudaMemcpyDeviceToHost, ms));
+    SF_CUDA(s, cudaStreamSynchronize(ms)); // the compute stream keeps integrating the interior bricks meanwhile
+    const uint32_t* T      = L.hostTable;
+    const uint32_t  sendLo = T[L.rank * kRowWords + 0], sendHi = T[L.rank * kRowWords + 1], nOwn = T[L.rank * kRowWords + 2];
+    const uint32_t  recvLo = hasLower ? T[(L.rank - 1) * kRowWords + 1] : 0u;
+    const uint32_t  recvHi = hasUpper ? T[(L.rank + 1) * kRowWords + 0] : 0u;
+    for(int r = 0; r < L.nranks; ++r)
+        if(T[r * kRowWords] > L.xcap || T[r * kRowWords + 1] > L.xcap) return fail(s, SF_ERR_STATE, "slab exchange buffer too small (load imbalance beyond the reserved capacity)");
+    if(static_cast<uint64_t>(n) + recvLo + recvHi > s->cap) return fail(s, SF_ERR_STATE, "slab particle capacity exceeded");
+    if(nc.GroupStart() != ncclSuccess) return fail(s, SF_ERR_COMM, "ncclGroupStart failed");
+    ncclResult_t r = ncclSuccess;
+    if(hasLower) {
+        if(sendLo && r == ncclSuccess) r = nc.Send(L.sendLo, static_cast<size_t>(sendLo) * 8, ncclFloat, L.rank - 1, L.comm, ms);
+        if(recvLo && r == ncclSuccess) r = nc.Recv(L.recvLo, static_cast<size_t>(recvLo) * 8, ncclFloat, L.rank - 1, L.comm, ms);
+    }
+    if(hasUpper) {
+        if(sendHi && r == ncclSuccess) r = nc.Send(L.sendHi, static_cast<size_t>(sendHi) * 8, ncclFloat, L.rank + 1, L.comm, ms);
+        if(recvHi && r == ncclSuccess) r = nc.Recv(L.recvHi, static_cast<size_t>(recvHi) * 8, ncclFloat, L.rank + 1, L.comm, ms);
+    }
+    if(nc.GroupEnd() != ncclSuccess || r != ncclSuccess) return fail(s, SF_ERR_COMM, "halo send/recv failed");
+    if(recvLo) k_slab_unpack<<<cdiv(recvLo, 256), 256, 0, ms>>>(L.recvLo, recvLo, B.posA + n, B.velA + n, B.idA + n);
+    if(recvHi) k_slab_unpack<<<cdiv(recvHi, 256), 256, 0, ms>>>(L.recvHi, recvHi, B.posA + n + recvLo, B.velA + n + recvLo, B.idA + n + recvLo);
+    SF_CUDA(s, cudaEventRecord(L.evExchanged, ms));
+    SF_CUDA(s, cudaStreamWaitEvent(cs, L.evExchanged, 0));
+    SF_CUDA(s, cudaGetLastError());
+    // ---- bookkeeping for the next substep: live = my integrated particles + received; dead = this substep's ghosts
+    s->nSlots = n + recvLo + recvHi;
+    s->n      = nOwn + recvLo + recvHi;
+    L.exchangedParticles += static_cast<uint64_t>(sendLo) + sendHi;
+    std::vector<int32_t> following = L.next;
+    slab_rebalance(T, kRowWords, L.nranks, s->grid[2], kMinThick, following.data());
+    L.cur  = L.next;
+    L.next = following;
+    L.nOwn = nOwn; // by the old bounds; exact count by the new bounds comes with the next table
+    return slab_configure_window(s);
+}
+
 } // namespace
 
 // =================================================================================================
@@ -439,6 +586,16 @@ void sf_destroy(sf_solver* s)
     cudaFree(B.cellTab); cudaFree(B.rho); cudaFree(B.rho2); cudaFree(B.accel); cudaFree(B.nbrL); cudaFree(B.nbrCnt); cudaFree(B.brickFlag); cudaFree(B.brickList);
     cudaFree(B.tabW); cudaFree(B.tabG); cudaFree(B.bnd); cudaFree(B.radixCounts); cudaFree(B.radixTotals); cudaFree(B.state);
     cudaFree(s->stage);
+    {
+        sf_solver::Slab& L = s->slab;
+        if(L.comm && nccl_api().CommDestroy) nccl_api().CommDestroy(L.comm);
+        cudaFree(L.sendLo); cudaFree(L.sendHi); cudaFree(L.recvLo); cudaFree(L.recvHi);
+        cudaFree(L.layerStart); cudaFree(L.counters); cudaFree(L.row); cudaFree(L.table);
+        if(L.hostTable) cudaFreeHost(L.hostTable);
+        if(L.evEdge) cudaEventDestroy(L.evEdge);
+        if(L.evExchanged) cudaEventDestroy(L.evExchanged);
+        if(L.commStream) cudaStreamDestroy(L.commStream);
+    }
     if(s->hostState) cudaFreeHost(s->hostState);
     if(s->timerA) cudaEventDestroy(s->timerA);
     if(s->timerB) cudaEventDestroy(s->timerB);
@@ -487,9 +644,10 @@ int sf_upload_particles(sf_solver* s, const float* pos_xyz, const float* vel_xyz
             return fail(s, SF_ERR_DOMAIN, buf);
         }
     }
+    if(s->slab.on) return fail(s, SF_ERR_INVALID, "slab mode: use sf_upload_particles_global");
     int rc = ensure_particle_capacity(s, n);
     if(rc) return rc;
-    s->n = n;
+    s->n = s->nSlots = n;
     if(n) {
         float* dpos = s->stage;
         float* dvel = s->stage + 3 * static_cast<size_t>(s->npad);
@@ -516,6 +674,7 @@ static int download_xyz(sf_solver* s, const float4* src, float* out)
 {
     if(!s || !out) return SF_ERR_INVALID;
     if(!s->uploaded) return fail(s, SF_ERR_INVALID, "no particles uploaded");
+    if(s->slab.on) return fail(s, SF_ERR_INVALID, "slab mode: use sf_download_owned");
     SF_CUDA(s, cudaSetDevice(s->device));
     if(s->n == 0) return SF_OK;
     {
@@ -565,8 +724,11 @@ int sf_make_ready(sf_solver* s)
     params_update(s->params);
     build_tables(s->params.kernelRadius, s->tables);
     grid_dims(s->params, s->grid);
-    s->ncells = static_cast<uint64_t>(s->grid[0]) * s->grid[1] * s->grid[2];
+    const int zPad = s->slab.on ? 2 * kGhost : 0; // slab mode: room for any window [zb - 3, ze + 3)
+    s->ncells = static_cast<uint64_t>(s->grid[0]) * s->grid[1] * (s->grid[2] + zPad);
     if(s->ncells == 0 || s->ncells >= (1ull << 31)) return fail(s, SF_ERR_INVALID, "grid has no cells or more than 2^31 cells");
+    if(s->slab.on && s->params.bCorrectDensity) return fail(s, SF_ERR_INVALID, "bCorrectDensity needs a fourth ghost layer: not supported with slabs");
+    if(s->slab.on && s->slab.cur.empty()) return fail(s, SF_ERR_INVALID, "slab mode: use sf_upload_particles_global");
     if(s->params.bUseBoundaryParticles && !s->wallsSet) {
         generate_boundary(s->params, 0u, s->walls); // the reference seeds from std::random_device; we default to seed 0
         s->wallsSet = true;
@@ -576,7 +738,7 @@ int sf_make_ready(sf_solver* s)
         s->cellCap = s->ncells;
     }
     {
-        const uint32_t nb = static_cast<uint32_t>((s->grid[0] + BX - 1) / BX) * ((s->grid[1] + BY - 1) / BY) * ((s->grid[2] + BZ - 1) / BZ);
+        const uint32_t nb = static_cast<uint32_t>((s->grid[0] + BX - 1) / BX) * ((s->grid[1] + BY - 1) / BY) * ((s->grid[2] + zPad + BZ - 1) / BZ);
         if(nb > s->brickCap || !s->B.brickFlag) {
             SF_CUDA(s, dev_alloc(s->B.brickFlag, nb + 1));
             SF_CUDA(s, dev_alloc(s->B.brickList, nb + 1));
@@ -604,13 +766,14 @@ int sf_make_ready(sf_solver* s)
 
     // radix-sort plan: ceil(log2(ncells)) key bits in passes of at most 8 bits
     int bits = 1;
-    while((1ull << bits) < s->ncells) ++bits;
+    while((1ull << bits) <= s->ncells) ++bits; // strictly more than ncells codes: the all-ones key marks dead slots
     s->sortPasses = (bits + 7) / 8;
     for(int i = 0, left = bits; i < s->sortPasses; ++i) {
         s->sortBits[i] = (left + (s->sortPasses - i) - 1) / (s->sortPasses - i);
         left -= s->sortBits[i];
     }
     fill_dev_params(s);
+    if(s->slab.on) slab_configure_window(s);
     // device state: step 0, both max-velocity slots at FLT_MIN, then computeMaxVel of the upload
     DevState init{};
     init.maxv2Bits[0] = init.maxv2Bits[1] = 0x00800000u; // FLT_MIN
@@ -845,6 +1008,8 @@ int sf_download_field(sf_solver* s, int field, void* out, uint64_t bytes)
     int rc = require_ready(s);
     if(rc) return rc;
     if(!out) return SF_ERR_INVALID;
+    if(s->slab.on && field != SF_FIELD_TABLE_CUBIC_W && field != SF_FIELD_TABLE_SPIKY_GRAD)
+        return fail(s, SF_ERR_INVALID, "per-particle fields are not gathered in slab mode");
     SF_CUDA(s, cudaSetDevice(s->device));
     SF_CUDA(s, cudaStreamSynchronize(s->stream));
     const uint32_t n = s->n;
@@ -871,7 +1036,7 @@ int sf_download_field(sf_solver* s, int field, void* out, uint64_t bytes)
         case SF_FIELD_PRESSURE: k_unpack_pressure<<<g, 256, 0, s->stream>>>(s->B.rho, s->B.idA, s->stage, s->P); break;
         case SF_FIELD_CELL_INDEX:
             if(!s->B.keyB) return fail(s, SF_ERR_INVALID, "no substep has run yet");
-            k_unpack_u32<<<g, 256, 0, s->stream>>>(s->B.keyB, s->B.idA, reinterpret_cast<uint32_t*>(s->stage), n);
+            k_unpack_u32<<<g, 256, 0, s->stream>>>(s->B.keyB, s->B.idA, reinterpret_cast<uint32_t*>(s->stage), n, 0u);
             break;
         case SF_FIELD_SORT_PERM:
             SF_CUDA(s, cudaMemcpy(out, s->B.idA, need, cudaMemcpyDeviceToHost));
@@ -955,13 +1120,178 @@ int sf_timer_stop(sf_solver* s, float* ms_out)
     return SF_OK;
 }
 
-// ---- multi-GPU (slab decomposition) -- implemented in sf_slab.cu when built --------------------
-#ifndef SF_WITH_SLAB
-int sf_comm_unique_id(void*) { return SF_ERR_INVALID; }
-int sf_comm_init(sf_solver* s, int, int, const void*) { return fail(s, SF_ERR_INVALID, "slab decomposition not built"); }
-int sf_upload_particles_global(sf_solver* s, const float*, const float*, uint32_t) { return fail(s, SF_ERR_INVALID, "slab decomposition not built"); }
-int sf_slab_info(sf_solver* s, int32_t*, int32_t*, uint32_t*, uint32_t*) { return fail(s, SF_ERR_INVALID, "slab decomposition not built"); }
-int sf_download_owned(sf_solver* s, uint32_t*, float*, float*, uint32_t, uint32_t*) { return fail(s, SF_ERR_INVALID, "slab decomposition not built"); }
-#endif
+// ---- multi-GPU: z-slab decomposition (design notes in sf_slab.cuh) -----------------------------
+int sf_comm_unique_id(void* id128)
+{
+    if(!id128) return SF_ERR_INVALID;
+    NcclApi& nc = nccl_api();
+    if(!nc.lib || !nc.GetUniqueId) return fail(nullptr, SF_ERR_COMM, "libnccl.so.2 not found");
+    ncclUniqueId id;
+    if(nc.GetUniqueId(&id) != ncclSuccess) return fail(nullptr, SF_ERR_COMM, "ncclGetUniqueId failed");
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    std::memcpy(id128, &id, 128);
+    return SF_OK;
+}
+
+int sf_comm_init(sf_solver* s, int rank, int nranks, const void* id128)
+{
+    if(!s || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return SF_ERR_INVALID;
+    if(nranks == 1) return SF_OK;
+    NcclApi& nc = nccl_api();
+    if(!nc.lib || !nc.CommInitRank) return fail(s, SF_ERR_COMM, "libnccl.so.2 not found");
+    SF_CUDA(s, cudaSetDevice(s->device));
+    ncclUniqueId id;
+    std::memcpy(&id, id128, 128);
+    ncclResult_t r = nc.CommInitRank(&s->slab.comm, nranks, id, rank);
+    if(r != ncclSuccess) return fail(s, SF_ERR_COMM, std::string("ncclCommInitRank: ") + nc.GetErrorString(r));
+    sf_solver::Slab& L = s->slab;
+    L.on     = true;
+    L.rank   = rank;
+    L.nranks = nranks;
+    int lo = 0, hi = 0;
+    SF_CUDA(s, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    SF_CUDA(s, cudaStreamCreateWithPriority(&L.commStream, cudaStreamNonBlocking, hi));
+    SF_CUDA(s, cudaEventCreateWithFlags(&L.evEdge, cudaEventDisableTiming));
+    SF_CUDA(s, cudaEventCreateWithFlags(&L.evExchanged, cudaEventDisableTiming));
+    SF_CUDA(s, dev_alloc(L.counters, 2));
+    SF_CUDA(s, dev_alloc(L.row, kRowWords));
+    SF_CUDA(s, dev_alloc(L.table, static_cast<size_t>(kRowWords) * nranks));
+    SF_CUDA(s, cudaMallocHost(reinterpret_cast<void**>(&L.hostTable), sizeof(uint32_t) * kRowWords * nranks));
+    return SF_OK;
+}
+
+int sf_upload_particles_global(sf_solver* s, const float* pos_xyz, const float* vel_xyz, uint32_t n_global)
+{
+    if(!s || (!pos_xyz && n_global)) return SF_ERR_INVALID;
+    if(!s->slab.on) return sf_upload_particles(s, pos_xyz, vel_xyz, n_global);
+    SF_CUDA(s, cudaSetDevice(s->device));
+    sf_solver::Slab& L = s->slab;
+    int32_t g[3];
+    grid_dims(s->params, g);
+    if(g[2] < L.nranks * kMinThick) return fail(s, SF_ERR_INVALID, "grid has too few cell layers for this many slabs");
+    std::vector<uint64_t> hist(g[2], 0);
+    std::vector<int32_t>  layer(n_global);
+    for(uint32_t i = 0; i < n_global; ++i) {
+        int32_t c[3];
+        if(!cell_coords_checked(s->params, g, pos_xyz + 3 * static_cast<size_t>(i), c)) return fail(s, SF_ERR_DOMAIN, "particle outside the simulation box");
+        layer[i] = c[2];
+        hist[c[2]]++;
+    }
+    L.cur.assign(L.nranks + 1, 0);
+    slab_plan(hist.data(), g[2], L.nranks, kMinThick, L.cur.data());
+    L.next = L.cur;
+    const int zb = L.cur[L.rank], ze = L.cur[L.rank + 1];
+    std::vector<float>    hp, hv;
+    std::vector<uint32_t> hid;
+    uint32_t              nOwn = 0;
+    for(uint32_t i = 0; i < n_global; ++i) {
+        if(layer[i] < zb - kGhost || layer[i] >= ze + kGhost) continue;
+        hp.insert(hp.end(), pos_xyz + 3 * static_cast<size_t>(i), pos_xyz + 3 * static_cast<size_t>(i) + 3);
+        if(vel_xyz) hv.insert(hv.end(), vel_xyz + 3 * static_cast<size_t>(i), vel_xyz + 3 * static_cast<size_t>(i) + 3);
+        hid.push_back(i);
+        nOwn += (layer[i] >= zb && layer[i] < ze) ? 1u : 0u;
+    }
+    const uint32_t n = static_cast<uint32_t>(hid.size());
+    // room for load-balance drift, ghosts and the dead slots of one substep
+    const uint32_t want = n + n / 2 + (1u << 18);
+    int rc = ensure_particle_capacity(s, want);
+    if(rc) return rc;
+    L.xcap = std::max<uint32_t>(want / 4, 1u << 16);
+    SF_CUDA(s, dev_alloc(L.sendLo, static_cast<size_t>(L.xcap) * 2));
+    SF_CUDA(s, dev_alloc(L.sendHi, static_cast<size_t>(L.xcap) * 2));
+    SF_CUDA(s, dev_alloc(L.recvLo, static_cast<size_t>(L.xcap) * 2));
+    SF_CUDA(s, dev_alloc(L.recvHi, static_cast<size_t>(L.xcap) * 2));
+    SF_CUDA(s, dev_alloc(L.layerStart, static_cast<size_t>(g[2]) + 2 * kGhost + 2));
+    if(n) {
+        float*    dpos = s->stage;
+        float*    dvel = s->stage + 3 * static_cast<size_t>(s->npad);
+        uint32_t* dids = s->B.keys[0]; // scratch until the first substep
+        SF_CUDA(s, cudaMemcpyAsync(dpos, hp.data(), static_cast<size_t>(n) * 12, cudaMemcpyHostToDevice, s->stream));
+        if(vel_xyz) SF_CUDA(s, cudaMemcpyAsync(dvel, hv.data(), static_cast<size_t>(n) * 12, cudaMemcpyHostToDevice, s->stream));
+        SF_CUDA(s, cudaMemcpyAsync(dids, hid.data(), static_cast<size_t>(n) * 4, cudaMemcpyHostToDevice, s->stream));
+        k_pack_upload_ids<<<cdiv(n, 256), 256, 0, s->stream>>>(dpos, vel_xyz ? dvel : nullptr, dids, s->B.posA, s->B.velA, s->B.idA, n);
+    }
+    SF_CUDA(s, cudaStreamSynchronize(s->stream));
+    s->n = s->nSlots = n;
+    L.nGlobal = n_global;
+    L.nOwn    = nOwn;
+    s->uploaded = true;
+    s->ready    = false;
+    return SF_OK;
+}
+
+int sf_slab_info(sf_solver* s, int32_t* z_begin, int32_t* z_end, uint32_t* n_owned, uint32_t* n_ghost)
+{
+    if(!s) return SF_ERR_INVALID;
+    if(!s->slab.on || s->slab.cur.empty()) {
+        if(z_begin) *z_begin = 0;
+        if(z_end) *z_end = s->grid[2];
+        if(n_owned) *n_owned = s->n;
+        if(n_ghost) *n_ghost = 0;
+        return SF_OK;
+    }
+    if(z_begin) *z_begin = s->slab.cur[s->slab.rank];
+    if(z_end) *z_end = s->slab.cur[s->slab.rank + 1];
+    if(n_owned) *n_owned = s->slab.nOwn;
+    if(n_ghost) *n_ghost = s->n - std::min(s->n, s->slab.nOwn);
+    return SF_OK;
+}
+
+int sf_download_owned(sf_solver* s, uint32_t* ids, float* pos_xyz, float* vel_xyz, uint32_t cap, uint32_t* n_out)
+{
+    if(!s || !n_out) return SF_ERR_INVALID;
+    if(!s->uploaded) return fail(s, SF_ERR_INVALID, "no particles uploaded");
+    SF_CUDA(s, cudaSetDevice(s->device));
+    SF_CUDA(s, cudaStreamSynchronize(s->stream));
+    const uint32_t      m = s->slab.on ? s->nSlots : s->n;
+    std::vector<float4> hx(m), hv(m);
+    std::vector<uint32_t> hid(m);
+    if(m) {
+        SF_CUDA(s, cudaMemcpy(hx.data(), s->B.posA, sizeof(float4) * m, cudaMemcpyDeviceToHost));
+        SF_CUDA(s, cudaMemcpy(hv.data(), s->B.velA, sizeof(float4) * m, cudaMemcpyDeviceToHost));
+        SF_CUDA(s, cudaMemcpy(hid.data(), s->B.idA, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost));
+    }
+    int32_t g[3];
+    grid_dims(s->params, g);
+    const int zb = s->slab.on ? s->slab.cur[s->slab.rank] : 0, ze = s->slab.on ? s->slab.cur[s->slab.rank + 1] : g[2];
+    uint32_t  k = 0;
+    for(uint32_t i = 0; i < m; ++i) {
+        if(hid[i] == kInvalidId) continue;
+        const int32_t lz = cell_layer(s->params, g[2], hx[i].z);
+        if(lz < zb || lz >= ze) continue;
+        if(k < cap) {
+            if(ids) ids[k] = hid[i];
+            if(pos_xyz) { pos_xyz[3 * k] = hx[i].x; pos_xyz[3 * k + 1] = hx[i].y; pos_xyz[3 * k + 2] = hx[i].z; }
+            if(vel_xyz) { vel_xyz[3 * k] = hv[i].x; vel_xyz[3 * k + 1] = hv[i].y; vel_xyz[3 * k + 2] = hv[i].z; }
+        }
+        ++k;
+    }
+    *n_out = k;
+    return SF_OK;
+}
+
+// host-side pieces of the decomposition, exposed for tests (no GPU needed)
+int sf_slab_plan(const uint64_t* layer_counts, int32_t nz, int32_t nranks, int32_t* cuts)
+{
+    if(!layer_counts || !cuts || nranks < 1 || nz < nranks * kMinThick) return SF_ERR_INVALID;
+    slab_plan(layer_counts, nz, nranks, kMinThick, cuts);
+    return SF_OK;
+}
+
+int sf_slab_rebalance(const uint32_t* table, int32_t nranks, int32_t nz, int32_t* cuts)
+{
+    if(!table || !cuts || nranks < 1) return SF_ERR_INVALID;
+    slab_rebalance(table, kRowWords, nranks, nz, kMinThick, cuts);
+    return SF_OK;
+}
+
+int sf_cell_layers(const sf_params* p, const float* pos_xyz, uint32_t n, int32_t* layers)
+{
+    if(!p || (!pos_xyz && n) || !layers) return SF_ERR_INVALID;
+    int32_t g[3];
+    grid_dims(*p, g);
+    for(uint32_t i = 0; i < n; ++i) layers[i] = cell_layer(*p, g[2], pos_xyz[3 * static_cast<size_t>(i) + 2]);
+    return SF_OK;
+}
 
 } // extern "C"

@@ -37,6 +37,14 @@ struct DevParams {
     int      kmax;
     int      nbx, nby, nbz; // brick grid
     uint32_t numBricks;
+    // z-slab decomposition (single GPU: z0 = 0, nzGlobal = nz, every range = [0, nz)).  nz above is the LOCAL
+    // number of cell layers; local layer l is global layer l + z0 (z0 may be negative at the bottom slab).
+    int      z0, nzGlobal;
+    int      zDensLo, zDensHi;   // local layers whose particles get a density / list
+    int      zForceLo, zForceHi; // ... a pressure force and v*
+    int      zOwnLo, zOwnHi;     // ... are integrated (owned by this rank)
+    int      zEdge;              // own layers within zEdge of a slab face are "boundary" for the overlapped exchange
+    int      slab;               // 1: slab mode
     uint32_t nbnd[6];     // wall particle counts
     uint32_t bndStride;   // slots per wall in the bnd array
 };

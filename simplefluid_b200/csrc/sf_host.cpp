@@ -228,6 +228,53 @@ bool cell_coords_checked(const sf_params& p, const int32_t n[3], const float* x,
     return true;
 }
 
+int32_t cell_layer(const sf_params& p, int32_t nz, float z)
+{
+    int32_t c = static_cast<int32_t>((z - p.boxMin[2]) / p.kernelRadius);
+    c         = c < nz - 1 ? c : nz - 1;
+    return c > 0 ? c : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// z-slab planning
+void slab_plan(const uint64_t* layerCounts, int32_t nz, int32_t nranks, int32_t minThick, int32_t* cuts)
+{
+    uint64_t total = 0;
+    for(int32_t z = 0; z < nz; ++z) total += layerCounts[z];
+    cuts[0]      = 0;
+    cuts[nranks] = nz;
+    uint64_t acc = 0;
+    int32_t  z   = 0;
+    for(int32_t r = 1; r < nranks; ++r) {
+        const uint64_t want = total * static_cast<uint64_t>(r) / static_cast<uint64_t>(nranks);
+        while(z < nz && acc + layerCounts[z] <= want) acc += layerCounts[z++];
+        // z = first layer that would overshoot: cut below or above it, whichever is closer to the target
+        int32_t cut = z;
+        if(z < nz && (want - acc) * 2 > layerCounts[z]) cut = z + 1;
+        const int32_t lo = cuts[r - 1] + minThick, hi = nz - (nranks - r) * minThick;
+        cut     = cut < lo ? lo : (cut > hi ? hi : cut);
+        cuts[r] = cut;
+        while(z < cut) acc += layerCounts[z++];
+    }
+}
+
+void slab_rebalance(const uint32_t* table, int32_t rowWords, int32_t nranks, int32_t nz, int32_t minThick, int32_t* cuts)
+{
+    (void)nz;
+    std::vector<int32_t> old(cuts, cuts + nranks + 1);
+    for(int32_t b = 1; b < nranks; ++b) {
+        const uint32_t* lower = table + static_cast<size_t>(b - 1) * rowWords;
+        const uint32_t* upper = table + static_cast<size_t>(b) * rowWords;
+        const int64_t   A = lower[2], Bc = upper[2];
+        const int64_t   topA = lower[4], botB = upper[3];
+        const int32_t   thickA = old[b] - old[b - 1], thickB = old[b + 1] - old[b];
+        // moving one layer changes the difference by twice that layer's population: move only past that hysteresis,
+        // and never let a slab lose two layers in one substep
+        if(A > Bc + 2 * topA && thickA > minThick + 1) cuts[b] = old[b] - 1;
+        else if(Bc > A + 2 * botB && thickB > minThick + 1) cuts[b] = old[b] + 1;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Wall patches (A.4): 6 walls x (nA x nA x nB) jittered points hanging outside the box; the patch
 // is expressed in wall-local tangential coordinates and follows the particle (A.6).

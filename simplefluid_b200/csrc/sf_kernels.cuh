@@ -107,17 +107,29 @@ __device__ __forceinline__ uint32_t cell_key(const DevParams& P, const float4& x
     int cz = static_cast<int>((x.z - P.bmin[2]) / P.h);
     cx     = max(min(cx, P.nx - 1), 0);
     cy     = max(min(cy, P.ny - 1), 0);
-    cz     = max(min(cz, P.nz - 1), 0);
+    cz     = max(min(cz, P.nzGlobal - 1), 0);
+    cz     = max(min(cz - P.z0, P.nz - 1), 0); // local layer of this rank's z-window (z0 = 0 on a single GPU)
     return static_cast<uint32_t>((cz * P.ny + cy) * P.nx + cx);
 }
 
-__global__ void k_hash(const float4* __restrict__ pos, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
-                       DevParams P, const DevState* st)
+// global cell layer of a position (A.7 z index), used by the slab exchange
+__device__ __forceinline__ int cell_layer_global(const DevParams& P, const float4& x)
+{
+    const int cz = static_cast<int>((x.z - P.bmin[2]) / P.h);
+    return max(min(cz, P.nzGlobal - 1), 0);
+}
+
+constexpr uint32_t kInvalidId = 0xffffffffu;
+
+// nSlots >= P.n in slab mode: dead slots (id == kInvalidId: last step's ghosts) get the maximal key and sort behind
+// the P.n live particles
+__global__ void k_hash(const float4* __restrict__ pos, const uint32_t* __restrict__ id, uint32_t* __restrict__ keys,
+                       uint32_t* __restrict__ vals, uint32_t nSlots, DevParams P, const DevState* st)
 {
     if(st->skip) return;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if(i >= P.n) return;
-    keys[i] = cell_key(P, pos[i]);
+    if(i >= nSlots) return;
+    keys[i] = id[i] == kInvalidId ? 0xffffffffu : cell_key(P, pos[i]);
     vals[i] = i;
 }
 
@@ -325,10 +337,10 @@ __global__ void k_unpack_scalar(const float* __restrict__ src, const uint32_t* _
     if(p < n) out[id[p]] = src[p];
 }
 
-__global__ void k_unpack_u32(const uint32_t* __restrict__ src, const uint32_t* __restrict__ id, uint32_t* __restrict__ out, uint32_t n)
+__global__ void k_unpack_u32(const uint32_t* __restrict__ src, const uint32_t* __restrict__ id, uint32_t* __restrict__ out, uint32_t n, uint32_t add)
 {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if(p < n) out[id[p]] = src[p];
+    if(p < n) out[id[p]] = src[p] + add;
 }
 
 __global__ void k_unpack_pressure(const float* __restrict__ rho, const uint32_t* __restrict__ id, float* __restrict__ out, DevParams P)
