@@ -179,16 +179,24 @@ def run_b200(args):
     if n_gpus not in res_by_n:
         raise SystemExit(f"workload {args.workload} is not defined for {n_gpus} GPUs")
     multi = n_gpus > 1
-    # weak scaling: until the slab path is active each rank advances its own ~8M-particle block
-    res = res_by_n[1] if multi and not getattr(sf, "HAS_SLAB", False) else res_by_n[n_gpus]
+    # weak scaling: ~8.09M particles per GPU; at N > 1 the ONE scene of N x 8M particles is cut into z-slabs
+    res = res_by_n[n_gpus]
     p = sf.default_params(res, scene)
     pos = sf.scene_generate(p)
-    n = len(pos)
+    n_total = len(pos)
 
     gpu = sf.SPHSolver(p, device=local)
-    gpu.setParticles(pos)
+    if multi:
+        from simplefluid_b200 import binding
+        uid = [binding.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        gpu.commInit(rank, world, uid[0])
+        gpu.setParticlesGlobal(pos)
+    else:
+        gpu.setParticles(pos)
     gpu.generateBoundaryParticles(0)
     gpu.makeReady()
+    n = n_total if not multi else gpu.slabInfo()[2]  # particles this rank owns
 
     # ---- device-resident throughput ------------------------------------------------------------
     gpu.advanceSteps(args.warmup)
@@ -213,21 +221,45 @@ def run_b200(args):
     gpu.profileEnable(False)
     clocks = sampler.stop() if rank == 0 else None
     ms = max_over_ranks(dist, ms, local)
-    total_particles = sum_over_ranks(dist, float(n), local)
+    total_particles = float(n_total)
     value = total_particles * args.steps / (ms * 1e-3)
 
     # ---- end to end through the host-buffer C-ABI call ------------------------------------------
     import torch
-    hx = torch.from_numpy(gpu.getParticles()).pin_memory()
-    hv = torch.from_numpy(gpu.getVelocity()).pin_memory()
     e2e_steps = max(3, min(args.steps, 20))
-    for _ in range(2):
-        gpu.stepHost(hx, hv)
-    barrier(dist)
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        gpu.stepHost(hx, hv)
-    e2e_s = max_over_ranks(dist, time.perf_counter() - t0, local)
+    if not multi:
+        hx = torch.from_numpy(gpu.getParticles()).pin_memory()
+        hv = torch.from_numpy(gpu.getVelocity()).pin_memory()
+        for _ in range(2):
+            gpu.stepHost(hx, hv)
+        barrier(dist)
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            gpu.stepHost(hx, hv)
+        e2e_s = max_over_ranks(dist, time.perf_counter() - t0, local)
+        h2d = d2h = 24 * n
+        e2e_api = "sf_step_host (pinned host buffers, upload + substep + download per step)"
+    else:
+        # every substep: this rank's resident slab state host -> device, one substep incl. the halo exchange, device -> host
+        cap = int(gpu.localSlots() * 1.3) + (1 << 18)
+        hx = torch.empty((cap, 4), dtype=torch.float32).pin_memory()
+        hv = torch.empty((cap, 4), dtype=torch.float32).pin_memory()
+        hi = torch.empty((cap,), dtype=torch.int32).pin_memory()
+        m = gpu.downloadLocal(hx, hv, hi)
+        moved = 0
+        for it in range(2 + e2e_steps):
+            if it == 2:
+                barrier(dist)
+                t0 = time.perf_counter()
+                moved = 0
+            gpu.uploadLocal(hx, hv, hi, m)
+            gpu.advanceFrame()
+            moved += 36 * m
+            m = gpu.downloadLocal(hx, hv, hi)
+            moved += 36 * m
+        e2e_s = max_over_ranks(dist, time.perf_counter() - t0, local)
+        h2d = d2h = int(sum_over_ranks(dist, float(moved), local) / (2 * e2e_steps))
+        e2e_api = "sf_upload_local + sf_advance_frame + sf_download_local (pinned host buffers, slab state of every rank, per step)"
     e2e_value = total_particles * e2e_steps / e2e_s
 
     if rank != 0:
@@ -239,7 +271,7 @@ def run_b200(args):
     step_kernels = {k: v for k, v in prof.items() if v[1] and k != "k_marshal"}
     dom = max(step_kernels, key=lambda k: step_kernels[k][0])
     dom_ms = step_kernels[dom][0] / step_kernels[dom][1]
-    dom_bytes = ALGO_BYTES.get(dom, 0.0) * n
+    dom_bytes = ALGO_BYTES.get(dom, 0.0) * n  # rank 0's own particles (its launch also covers the ghost layers)
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
     step_achieved = ALGO_BYTES["step"] * (value / n_gpus) / 1e9
     traffic = None
@@ -263,12 +295,12 @@ def run_b200(args):
         "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": n_gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "scene": scene, "resolution": res, "particles_per_gpu": n,
+        "config": {"workload": args.workload, "scene": scene, "resolution": res, "particles_per_gpu": int(total_particles // n_gpus),
                    "particles_total": int(total_particles), "grid_cells": int(np.prod(gpu.gridDims())),
-                   "parallelism": ("replicas" if multi else "single") if not getattr(sf, "HAS_SLAB", False) else f"zslab{n_gpus}",
+                   "parallelism": f"zslab{n_gpus} (3-layer ghost halo, 1 NCCL exchange + 1 allreduce per substep)" if multi else "single",
                    "l2": "inputs_exceed_l2" if n * 100 > 126e6 else "state_fits_l2_not_flushed", "boundary_seed": 0},
-        "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": 24 * n, "d2h_bytes_per_step": 24 * n,
-                "steps": e2e_steps, "api": "sf_step_host (pinned host buffers, upload + substep + download per step)"},
+        "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "api": e2e_api},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -163,6 +163,9 @@ int sf_upload_particles_global(sf_solver* s, const float* pos_xyz, const float* 
 int sf_slab_info(sf_solver* s, int32_t* z_begin, int32_t* z_end, uint32_t* n_owned, uint32_t* n_ghost);
 /* Owned particles with their global (original) ids. */
 int sf_download_owned(sf_solver* s, uint32_t* ids, float* pos_xyz, float* vel_xyz, uint32_t cap, uint32_t* n_out);
+/* Raw resident state of this rank (float4 positions/velocities + ids, all slots) to / from host buffers. */
+int sf_download_local(sf_solver* s, float* pos4, float* vel4, uint32_t* ids, uint32_t cap, uint32_t* n_out);
+int sf_upload_local(sf_solver* s, const float* pos4, const float* vel4, const uint32_t* ids, uint32_t n);
 /* Host-side pieces of the decomposition (no GPU needed): count-balanced cut planes (cuts[nranks+1]) from a
  * per-layer particle histogram; the one-layer-per-substep rebalancing rule applied to the all-gathered table
  * (8 uint32 per rank: sendLo, sendHi, nOwn, firstLayerCount, lastLayerCount, ...); global cell layer per particle. */

@@ -13,5 +13,7 @@ from .binding import (  # noqa: F401
     SCENES, SFError, SFParams, SPHSolver, build_library, default_params, library, library_path, scene_generate,
 )
 
-__all__ = ["SCENES", "SFError", "SFParams", "SPHSolver", "build_library", "default_params", "library",
+HAS_SLAB = True  # multi-GPU z-slab decomposition is built into the library
+
+__all__ = ["HAS_SLAB", "SCENES", "SFError", "SFParams", "SPHSolver", "build_library", "default_params", "library",
            "library_path", "scene_generate"]

@@ -25,7 +25,7 @@ EXPORTS = [
     "sf_synchronize", "sf_step_host", "sf_set_capture", "sf_field_size", "sf_download_field", "sf_grid_dims",
     "sf_profile_enable", "sf_profile_reset", "sf_profile_get", "sf_launch_count", "sf_timer_start", "sf_timer_stop",
     "sf_comm_unique_id", "sf_comm_init", "sf_upload_particles_global", "sf_slab_info", "sf_download_owned",
-    "sf_slab_plan", "sf_slab_rebalance", "sf_cell_layers",
+    "sf_slab_plan", "sf_slab_rebalance", "sf_cell_layers", "sf_download_local", "sf_upload_local",
 ]
 
 
@@ -102,6 +102,7 @@ def library():
         "sf_upload_particles_global": [vp, vp, vp, u32],
         "sf_slab_info": [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(u32), C.POINTER(u32)],
         "sf_download_owned": [vp, vp, vp, vp, u32, C.POINTER(u32)],
+        "sf_download_local": [vp, vp, vp, vp, u32, C.POINTER(u32)], "sf_upload_local": [vp, vp, vp, vp, u32],
         "sf_slab_plan": [vp, i32, i32, vp], "sf_slab_rebalance": [vp, i32, i32, vp], "sf_cell_layers": [PP, vp, u32, vp],
     }
     for name, argtypes in sig.items():
@@ -366,6 +367,19 @@ class SPHSolver:
         v = np.empty((n.value, 3), np.float32)
         self._ck(self.L.sf_download_owned(self.h, ids.ctypes.data, x.ctypes.data, v.ctypes.data, n.value, C.byref(n)))
         return ids, x, v
+
+    def localSlots(self):
+        n = C.c_uint32(0)
+        self._ck(self.L.sf_download_local(self.h, None, None, None, 0, C.byref(n)))
+        return n.value
+
+    def downloadLocal(self, pos4, vel4, ids):
+        n = C.c_uint32(0)
+        self._ck(self.L.sf_download_local(self.h, _ptr(pos4), _ptr(vel4), _ptr(ids), ids.shape[0], C.byref(n)))
+        return n.value
+
+    def uploadLocal(self, pos4, vel4, ids, n):
+        self._ck(self.L.sf_upload_local(self.h, _ptr(pos4), _ptr(vel4), _ptr(ids), n))
 
     # -- measurement
     def profileEnable(self, on=True):

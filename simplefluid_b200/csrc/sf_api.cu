@@ -5,8 +5,10 @@
 // with no host synchronisation: dt, the frame-time accumulator and the max-velocity reduction all
 // live in a DevState block on the device.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -78,6 +80,8 @@ struct sf_solver {
         uint32_t             nOwn = 0;
         uint64_t             ncellsMax = 0;
         uint64_t             exchangedParticles = 0;
+        double               tWaitPack = 0, tPost = 0, tFront = 0; // host seconds: waiting for the table / posting the exchange / enqueueing
+        uint64_t             steps = 0;
     } slab;
 
     // measurement
@@ -314,7 +318,7 @@ int enqueue_substep(sf_solver* s)
     }
     {
         LaunchScope ls(s, K_BRICK_COMPACT);
-        k_brick_compact<<<1, 1024, 0, st>>>(B.brickFlag, B.brickList, s->numBricks, B.state);
+        k_brick_compact<<<cdiv(s->numBricks, 1024), 1024, 0, st>>>(B.brickFlag, B.brickList, s->numBricks, B.state);
     }
     if(slab) k_layer_start<<<cdiv(static_cast<uint32_t>(P.nz) + 1u, 128), 128, 0, st>>>(B.keyB, n, P, s->slab.layerStart);
     const uint32_t pairGrid = std::max<uint32_t>(1u, std::min<uint32_t>(s->numBricks, static_cast<uint32_t>(s->numSMs) * 2u));
@@ -434,7 +438,10 @@ int slab_exchange(sf_solver* s, uint32_t n, uint32_t nSlots)
     k_slab_row<<<1, 1, 0, ms>>>(L.layerStart, L.counters, P, L.row);
     if(nc.AllGather(L.row, L.table, kRowWords, ncclUint32, L.comm, ms) != ncclSuccess) return fail(s, SF_ERR_COMM, "ncclAllGather failed");
     SF_CUDA(s, cudaMemcpyAsync(L.hostTable, L.table, sizeof(uint32_t) * kRowWords * L.nranks, cudaMemcpyDeviceToHost, ms));
+    const auto tw0 = std::chrono::steady_clock::now();
     SF_CUDA(s, cudaStreamSynchronize(ms)); // the compute stream keeps integrating the interior bricks meanwhile
+    const auto tw1 = std::chrono::steady_clock::now();
+    L.tWaitPack += std::chrono::duration<double>(tw1 - tw0).count();
     const uint32_t* T      = L.hostTable;
     const uint32_t  sendLo = T[L.rank * kRowWords + 0], sendHi = T[L.rank * kRowWords + 1], nOwn = T[L.rank * kRowWords + 2];
     const uint32_t  recvLo = hasLower ? T[(L.rank - 1) * kRowWords + 1] : 0u;
@@ -467,6 +474,8 @@ int slab_exchange(sf_solver* s, uint32_t n, uint32_t nSlots)
     L.cur  = L.next;
     L.next = following;
     L.nOwn = nOwn; // by the old bounds; exact count by the new bounds comes with the next table
+    L.tPost += std::chrono::duration<double>(std::chrono::steady_clock::now() - tw1).count();
+    L.steps++;
     return slab_configure_window(s);
 }
 
@@ -588,6 +597,9 @@ void sf_destroy(sf_solver* s)
     cudaFree(s->stage);
     {
         sf_solver::Slab& L = s->slab;
+        if(L.on && L.steps && std::getenv("SF_SLAB_TRACE"))
+            std::fprintf(stderr, "[sf slab rank %d] %llu substeps: host wait for edge+pack+allgather %.3f ms/step, post exchange %.3f ms/step, exchanged %.1f particles/step\n",
+                         L.rank, (unsigned long long)L.steps, L.tWaitPack / L.steps * 1e3, L.tPost / L.steps * 1e3, double(L.exchangedParticles) / L.steps);
         if(L.comm && nccl_api().CommDestroy) nccl_api().CommDestroy(L.comm);
         cudaFree(L.sendLo); cudaFree(L.sendHi); cudaFree(L.recvLo); cudaFree(L.recvHi);
         cudaFree(L.layerStart); cudaFree(L.counters); cudaFree(L.row); cudaFree(L.table);
@@ -1267,6 +1279,33 @@ int sf_download_owned(sf_solver* s, uint32_t* ids, float* pos_xyz, float* vel_xy
         ++k;
     }
     *n_out = k;
+    return SF_OK;
+}
+
+// raw local state (live + dead slots) <-> host: what bench.py's multi-GPU e2e leg moves every substep
+int sf_download_local(sf_solver* s, float* pos4, float* vel4, uint32_t* ids, uint32_t cap, uint32_t* n_out)
+{
+    if(!s || !n_out) return SF_ERR_INVALID;
+    SF_CUDA(s, cudaSetDevice(s->device));
+    const uint32_t m = s->slab.on ? s->nSlots : s->n;
+    *n_out = m;
+    if(m > cap || !pos4 || !vel4 || !ids) return m > cap ? fail(s, SF_ERR_INVALID, "buffer too small") : SF_OK;
+    SF_CUDA(s, cudaMemcpyAsync(pos4, s->B.posA, sizeof(float4) * m, cudaMemcpyDeviceToHost, s->stream));
+    SF_CUDA(s, cudaMemcpyAsync(vel4, s->B.velA, sizeof(float4) * m, cudaMemcpyDeviceToHost, s->stream));
+    SF_CUDA(s, cudaMemcpyAsync(ids, s->B.idA, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost, s->stream));
+    SF_CUDA(s, cudaStreamSynchronize(s->stream));
+    return SF_OK;
+}
+
+int sf_upload_local(sf_solver* s, const float* pos4, const float* vel4, const uint32_t* ids, uint32_t n)
+{
+    if(!s || !pos4 || !vel4 || !ids) return SF_ERR_INVALID;
+    SF_CUDA(s, cudaSetDevice(s->device));
+    const uint32_t m = s->slab.on ? s->nSlots : s->n;
+    if(n != m) return fail(s, SF_ERR_INVALID, "sf_upload_local: slot count must match the resident state");
+    SF_CUDA(s, cudaMemcpyAsync(s->B.posA, pos4, sizeof(float4) * m, cudaMemcpyHostToDevice, s->stream));
+    SF_CUDA(s, cudaMemcpyAsync(s->B.velA, vel4, sizeof(float4) * m, cudaMemcpyHostToDevice, s->stream));
+    SF_CUDA(s, cudaMemcpyAsync(s->B.idA, ids, sizeof(uint32_t) * m, cudaMemcpyHostToDevice, s->stream));
     return SF_OK;
 }
 

@@ -73,6 +73,8 @@ __global__ void k_begin_step(DevState* st, DevParams P)
         return;
     }
     st->skip          = 0;
+    st->brickCount    = 0u;
+    st->cursor[0] = st->cursor[1] = st->cursor[2] = st->cursor[3] = 0u;
     const unsigned pr = st->step & 1u;
     const float    M  = __uint_as_float(st->maxv2Bits[pr]);
     const float    maxv = sqrtf(M);

@@ -1,0 +1,28 @@
+"""Multi-GPU parity (needs >= 2 B200s; skipped on a single-GPU box): the z-slab run, gathered by global particle id,
+must be bit-identical to a single-GPU run of the same scene (tools/mgpu_check.py under torchrun)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpu():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.parametrize("world,scene,res,steps", [(2, "Dambreak", 32, 300), (4, "DoubleDambreak", 48, 120)])
+def test_slabs_bit_identical_to_single_gpu(sf, world, scene, res, steps):
+    if _ngpu() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29600 + world), os.path.join(ROOT, "tools", "mgpu_check.py"), scene, str(res), str(steps)]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "MGPU OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
