@@ -241,7 +241,7 @@ def run_b200(args):
         e2e_api = "sf_step_host (pinned host buffers, upload + substep + download per step)"
     else:
         # every substep: this rank's resident slab state host -> device, one substep incl. the halo exchange, device -> host
-        cap = int(gpu.localSlots() * 1.3) + (1 << 18)
+        cap = 2 * gpu.localSlots() + (1 << 20)
         hx = torch.empty((cap, 4), dtype=torch.float32).pin_memory()
         hv = torch.empty((cap, 4), dtype=torch.float32).pin_memory()
         hi = torch.empty((cap,), dtype=torch.int32).pin_memory()
@@ -287,9 +287,9 @@ def run_b200(args):
     if n_gpus == 1 and not args.no_cpu_baseline:
         sres = REFERENCE_SAMPLE_RES[scene] if args.workload != "dambreak_default" else 24
         cores = os.cpu_count() or 1
-        cv, cn, secs = cpu_oracle_run(scene, sres, 6, 1)
+        cv, cn, secs = cpu_oracle_run(scene, sres, 80, 2)
         cpu = {"value": cv, "unit": "particle-steps/s", "cores": cores, "kind": "port",
-               "sample": f"{scene} res {sres} ({cn} particles) x 6 substeps in {secs:.1f} s, OpenMP {cores} threads"}
+               "sample": f"{scene} res {sres} ({cn} particles) x 80 substeps in {secs:.1f} s, OpenMP {cores} threads"}
 
     line = {
         "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": n_gpus, "steps": args.steps,

@@ -63,6 +63,9 @@ struct sf_solver {
     int          occDensity = 1, occForce = 1, occVisc = 1;
     uint32_t     numBricks = 0, brickCap = 0;
     uint32_t     nSlots = 0; // live + dead slots of the A arrays (== n on a single GPU)
+    int          axisS = 2;  // slow axis of the cell key: 2 = z (reference order), 1 = y (slab runs that are longer in y)
+    int32_t      nS() const { return grid[axisS]; }
+    int32_t      nM() const { return grid[3 - axisS]; }
 
     // z-slab decomposition (sf_comm_init)
     struct Slab {
@@ -200,8 +203,9 @@ void fill_dev_params(sf_solver* s)
     P.dtMin        = p.defaultTimestep * 0.1f;
     P.dtMax        = p.defaultTimestep * 10.0f;
     P.nx = s->grid[0];
-    P.ny = s->grid[1];
-    P.nz = s->grid[2];
+    P.ny = s->nM();
+    P.nz = s->nS();
+    P.axisS = s->axisS;
     P.useBoundary    = p.bUseBoundaryParticles ? 1 : 0;
     P.attractive     = p.bUseAttractivePressure ? 1 : 0;
     P.correctDensity = p.bCorrectDensity ? 1 : 0;
@@ -210,13 +214,13 @@ void fill_dev_params(sf_solver* s)
     P.npad = s->npad;
     P.kmax = s->kmax;
     P.nbx  = (s->grid[0] + BX - 1) / BX;
-    P.nby  = (s->grid[1] + BY - 1) / BY;
-    P.nbz  = (s->grid[2] + BZ - 1) / BZ;
+    P.nby  = (s->nM() + BY - 1) / BY;
+    P.nbz  = (s->nS() + BZ - 1) / BZ;
     P.numBricks = s->numBricks;
     P.z0 = 0;
-    P.nzGlobal = s->grid[2];
+    P.nzGlobal = s->nS();
     P.zDensLo = P.zForceLo = P.zOwnLo = 0;
-    P.zDensHi = P.zForceHi = P.zOwnHi = s->grid[2];
+    P.zDensHi = P.zForceHi = P.zOwnHi = s->nS();
     P.zEdge = 0;
     P.slab  = 0;
     for(int w = 0; w < 6; ++w) P.nbnd[w] = P.useBoundary ? static_cast<uint32_t>(s->walls[w].size() / 3) : 0u;
@@ -381,15 +385,15 @@ int slab_configure_window(sf_solver* s)
     sf_solver::Slab& L = s->slab;
     const int zb = L.cur[L.rank], ze = L.cur[L.rank + 1];
     const int nzL = ze - zb + 2 * kGhost;
-    s->ncells    = static_cast<uint64_t>(s->grid[0]) * s->grid[1] * nzL;
-    s->numBricks = static_cast<uint32_t>((s->grid[0] + BX - 1) / BX) * ((s->grid[1] + BY - 1) / BY) * ((nzL + BZ - 1) / BZ);
+    s->ncells    = static_cast<uint64_t>(s->grid[0]) * s->nM() * nzL;
+    s->numBricks = static_cast<uint32_t>((s->grid[0] + BX - 1) / BX) * ((s->nM() + BY - 1) / BY) * ((nzL + BZ - 1) / BZ);
     fill_dev_params(s);
     DevParams& P = s->P;
     P.nz        = nzL;
     P.nbz       = (nzL + BZ - 1) / BZ;
     P.numBricks = s->numBricks;
     P.z0        = zb - kGhost;
-    P.nzGlobal  = s->grid[2];
+    P.nzGlobal  = s->nS();
     P.zDensLo = 1;
     P.zDensHi = nzL - 1;
     P.zForceLo = 2;
@@ -470,7 +474,7 @@ int slab_exchange(sf_solver* s, uint32_t n, uint32_t nSlots)
     s->n      = nOwn + recvLo + recvHi;
     L.exchangedParticles += static_cast<uint64_t>(sendLo) + sendHi;
     std::vector<int32_t> following = L.next;
-    slab_rebalance(T, kRowWords, L.nranks, s->grid[2], kMinThick, following.data());
+    slab_rebalance(T, kRowWords, L.nranks, s->nS(), kMinThick, following.data());
     L.cur  = L.next;
     L.next = following;
     L.nOwn = nOwn; // by the old bounds; exact count by the new bounds comes with the next table
@@ -737,7 +741,8 @@ int sf_make_ready(sf_solver* s)
     build_tables(s->params.kernelRadius, s->tables);
     grid_dims(s->params, s->grid);
     const int zPad = s->slab.on ? 2 * kGhost : 0; // slab mode: room for any window [zb - 3, ze + 3)
-    s->ncells = static_cast<uint64_t>(s->grid[0]) * s->grid[1] * (s->grid[2] + zPad);
+    if(!s->slab.on) s->axisS = 2;
+    s->ncells = static_cast<uint64_t>(s->grid[0]) * s->nM() * (s->nS() + zPad);
     if(s->ncells == 0 || s->ncells >= (1ull << 31)) return fail(s, SF_ERR_INVALID, "grid has no cells or more than 2^31 cells");
     if(s->slab.on && s->params.bCorrectDensity) return fail(s, SF_ERR_INVALID, "bCorrectDensity needs a fourth ghost layer: not supported with slabs");
     if(s->slab.on && s->slab.cur.empty()) return fail(s, SF_ERR_INVALID, "slab mode: use sf_upload_particles_global");
@@ -750,7 +755,7 @@ int sf_make_ready(sf_solver* s)
         s->cellCap = s->ncells;
     }
     {
-        const uint32_t nb = static_cast<uint32_t>((s->grid[0] + BX - 1) / BX) * ((s->grid[1] + BY - 1) / BY) * ((s->grid[2] + zPad + BZ - 1) / BZ);
+        const uint32_t nb = static_cast<uint32_t>((s->grid[0] + BX - 1) / BX) * ((s->nM() + BY - 1) / BY) * ((s->nS() + zPad + BZ - 1) / BZ);
         if(nb > s->brickCap || !s->B.brickFlag) {
             SF_CUDA(s, dev_alloc(s->B.brickFlag, nb + 1));
             SF_CUDA(s, dev_alloc(s->B.brickList, nb + 1));
@@ -1180,17 +1185,27 @@ int sf_upload_particles_global(sf_solver* s, const float* pos_xyz, const float* 
     sf_solver::Slab& L = s->slab;
     int32_t g[3];
     grid_dims(s->params, g);
-    if(g[2] < L.nranks * kMinThick) return fail(s, SF_ERR_INVALID, "grid has too few cell layers for this many slabs");
-    std::vector<uint64_t> hist(g[2], 0);
-    std::vector<int32_t>  layer(n_global);
+    std::vector<uint64_t> histY(g[1], 0), histZ(g[2], 0);
+    std::vector<int32_t>  layerY(n_global), layerZ(n_global);
     for(uint32_t i = 0; i < n_global; ++i) {
         int32_t c[3];
         if(!cell_coords_checked(s->params, g, pos_xyz + 3 * static_cast<size_t>(i), c)) return fail(s, SF_ERR_DOMAIN, "particle outside the simulation box");
-        layer[i] = c[2];
-        hist[c[2]]++;
+        layerY[i] = c[1];
+        layerZ[i] = c[2];
+        histY[c[1]]++;
+        histZ[c[2]]++;
     }
+    // slab axis = the slow axis (y or z) along which the particle set spans more cell layers: thicker slabs, so the
+    // 3 + 3 ghost layers weigh less.  Every rank sees the same input and takes the same decision.
+    auto occupied = [](const std::vector<uint64_t>& h) { size_t k = 0; for(uint64_t v : h) k += v ? 1 : 0; return k; };
+    if(const char* force = std::getenv("SF_SLAB_AXIS")) s->axisS = (force[0] == 'y' || force[0] == 'Y' || force[0] == '1') ? 1 : 2;
+    else s->axisS = occupied(histY) > occupied(histZ) ? 1 : 2;
+    const std::vector<uint64_t>& hist  = s->axisS == 1 ? histY : histZ;
+    const std::vector<int32_t>&  layer = s->axisS == 1 ? layerY : layerZ;
+    s->grid[0] = g[0]; s->grid[1] = g[1]; s->grid[2] = g[2];
+    if(s->nS() < L.nranks * kMinThick) return fail(s, SF_ERR_INVALID, "grid has too few cell layers for this many slabs");
     L.cur.assign(L.nranks + 1, 0);
-    slab_plan(hist.data(), g[2], L.nranks, kMinThick, L.cur.data());
+    slab_plan(hist.data(), s->nS(), L.nranks, kMinThick, L.cur.data());
     L.next = L.cur;
     const int zb = L.cur[L.rank], ze = L.cur[L.rank + 1];
     std::vector<float>    hp, hv;
@@ -1213,7 +1228,7 @@ int sf_upload_particles_global(sf_solver* s, const float* pos_xyz, const float* 
     SF_CUDA(s, dev_alloc(L.sendHi, static_cast<size_t>(L.xcap) * 2));
     SF_CUDA(s, dev_alloc(L.recvLo, static_cast<size_t>(L.xcap) * 2));
     SF_CUDA(s, dev_alloc(L.recvHi, static_cast<size_t>(L.xcap) * 2));
-    SF_CUDA(s, dev_alloc(L.layerStart, static_cast<size_t>(g[2]) + 2 * kGhost + 2));
+    SF_CUDA(s, dev_alloc(L.layerStart, static_cast<size_t>(std::max(g[1], g[2])) + 2 * kGhost + 2));
     if(n) {
         float*    dpos = s->stage;
         float*    dvel = s->stage + 3 * static_cast<size_t>(s->npad);
@@ -1237,7 +1252,7 @@ int sf_slab_info(sf_solver* s, int32_t* z_begin, int32_t* z_end, uint32_t* n_own
     if(!s) return SF_ERR_INVALID;
     if(!s->slab.on || s->slab.cur.empty()) {
         if(z_begin) *z_begin = 0;
-        if(z_end) *z_end = s->grid[2];
+        if(z_end) *z_end = s->nS();
         if(n_owned) *n_owned = s->n;
         if(n_ghost) *n_ghost = 0;
         return SF_OK;
@@ -1265,11 +1280,11 @@ int sf_download_owned(sf_solver* s, uint32_t* ids, float* pos_xyz, float* vel_xy
     }
     int32_t g[3];
     grid_dims(s->params, g);
-    const int zb = s->slab.on ? s->slab.cur[s->slab.rank] : 0, ze = s->slab.on ? s->slab.cur[s->slab.rank + 1] : g[2];
+    const int zb = s->slab.on ? s->slab.cur[s->slab.rank] : 0, ze = s->slab.on ? s->slab.cur[s->slab.rank + 1] : g[s->axisS];
     uint32_t  k = 0;
     for(uint32_t i = 0; i < m; ++i) {
         if(hid[i] == kInvalidId) continue;
-        const int32_t lz = cell_layer(s->params, g[2], hx[i].z);
+        const int32_t lz = cell_layer(s->params, g[s->axisS], s->axisS == 1 ? hx[i].y : hx[i].z, s->axisS);
         if(lz < zb || lz >= ze) continue;
         if(k < cap) {
             if(ids) ids[k] = hid[i];
@@ -1289,7 +1304,8 @@ int sf_download_local(sf_solver* s, float* pos4, float* vel4, uint32_t* ids, uin
     SF_CUDA(s, cudaSetDevice(s->device));
     const uint32_t m = s->slab.on ? s->nSlots : s->n;
     *n_out = m;
-    if(m > cap || !pos4 || !vel4 || !ids) return m > cap ? fail(s, SF_ERR_INVALID, "buffer too small") : SF_OK;
+    if(!pos4 || !vel4 || !ids) return SF_OK; // count query
+    if(m > cap) return fail(s, SF_ERR_INVALID, "buffer too small");
     SF_CUDA(s, cudaMemcpyAsync(pos4, s->B.posA, sizeof(float4) * m, cudaMemcpyDeviceToHost, s->stream));
     SF_CUDA(s, cudaMemcpyAsync(vel4, s->B.velA, sizeof(float4) * m, cudaMemcpyDeviceToHost, s->stream));
     SF_CUDA(s, cudaMemcpyAsync(ids, s->B.idA, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost, s->stream));

@@ -45,6 +45,11 @@ struct DevParams {
     int      zOwnLo, zOwnHi;     // ... are integrated (owned by this rank)
     int      zEdge;              // own layers within zEdge of a slab face are "boundary" for the overlapped exchange
     int      slab;               // 1: slab mode
+    // Key order is (slow * ny + mid) * nx + x.  The slow axis is z (axisS = 2, the reference's own order) or, for
+    // slab runs whose particles span more layers in y, y (axisS = 1); then ny/nz above hold the MID / SLOW axis
+    // cell counts and every "z"/"layer" of the slab logic means the slow axis.  The 3x3 rows of a neighbourhood
+    // are always visited in the reference's order (dz outer, dy inner).
+    int      axisS;
     uint32_t nbnd[6];     // wall particle counts
     uint32_t bndStride;   // slots per wall in the bnd array
 };

@@ -228,10 +228,10 @@ bool cell_coords_checked(const sf_params& p, const int32_t n[3], const float* x,
     return true;
 }
 
-int32_t cell_layer(const sf_params& p, int32_t nz, float z)
+int32_t cell_layer(const sf_params& p, int32_t n, float coord, int axis)
 {
-    int32_t c = static_cast<int32_t>((z - p.boxMin[2]) / p.kernelRadius);
-    c         = c < nz - 1 ? c : nz - 1;
+    int32_t c = static_cast<int32_t>((coord - p.boxMin[axis]) / p.kernelRadius);
+    c         = c < n - 1 ? c : n - 1;
     return c > 0 ? c : 0;
 }
 

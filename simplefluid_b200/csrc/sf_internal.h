@@ -29,7 +29,7 @@ void grid_dims(const sf_params& p, int32_t n[3]);
 bool cell_coords_checked(const sf_params& p, const int32_t n[3], const float* x, int32_t c[3]);
 void generate_boundary(const sf_params& p, uint32_t seed, std::vector<float> walls[6]);
 // global cell layer (A.7 z index, clamped) of a z coordinate -- same float ops as the device hash
-int32_t cell_layer(const sf_params& p, int32_t nz, float z);
+int32_t cell_layer(const sf_params& p, int32_t n, float coord, int axis = 2);
 // z-slab decomposition (no counterpart in the reference): count-balanced cut planes with a minimum thickness, and
 // the one-layer-per-substep rebalancing rule every rank evaluates identically from the all-gathered table
 // (row r = {sendLo, sendHi, nOwn, firstLayerCount, lastLayerCount, ...}, rowWords words per row)

@@ -104,21 +104,22 @@ __global__ void k_init_maxvel(const float4* __restrict__ vel, uint32_t n, DevSta
 // (1) cell hashing: collectParticlesToCells' index expression (A.7), bit-exact
 __device__ __forceinline__ uint32_t cell_key(const DevParams& P, const float4& x)
 {
+    const int axisM = 3 - P.axisS;
     int cx = static_cast<int>((x.x - P.bmin[0]) / P.h);
-    int cy = static_cast<int>((x.y - P.bmin[1]) / P.h);
-    int cz = static_cast<int>((x.z - P.bmin[2]) / P.h);
+    int cm = static_cast<int>((comp(x, axisM) - P.bmin[axisM]) / P.h);
+    int cs = static_cast<int>((comp(x, P.axisS) - P.bmin[P.axisS]) / P.h);
     cx     = max(min(cx, P.nx - 1), 0);
-    cy     = max(min(cy, P.ny - 1), 0);
-    cz     = max(min(cz, P.nzGlobal - 1), 0);
-    cz     = max(min(cz - P.z0, P.nz - 1), 0); // local layer of this rank's z-window (z0 = 0 on a single GPU)
-    return static_cast<uint32_t>((cz * P.ny + cy) * P.nx + cx);
+    cm     = max(min(cm, P.ny - 1), 0);
+    cs     = max(min(cs, P.nzGlobal - 1), 0);
+    cs     = max(min(cs - P.z0, P.nz - 1), 0); // local layer of this rank's window (z0 = 0 on a single GPU)
+    return static_cast<uint32_t>((cs * P.ny + cm) * P.nx + cx);
 }
 
-// global cell layer of a position (A.7 z index), used by the slab exchange
+// global cell layer of a position along the slow axis (A.7 index, clamped), used by the slab exchange
 __device__ __forceinline__ int cell_layer_global(const DevParams& P, const float4& x)
 {
-    const int cz = static_cast<int>((x.z - P.bmin[2]) / P.h);
-    return max(min(cz, P.nzGlobal - 1), 0);
+    const int cs = static_cast<int>((comp(x, P.axisS) - P.bmin[P.axisS]) / P.h);
+    return max(min(cs, P.nzGlobal - 1), 0);
 }
 
 constexpr uint32_t kInvalidId = 0xffffffffu;
