@@ -123,6 +123,16 @@ int sf_synchronize(sf_solver* s);
  * download pos/vel into the same buffers. */
 int sf_step_host(sf_solver* s, float* pos_xyz, float* vel_xyz, uint32_t n, float* dt_out);
 
+/* ---- renderer hand-off and checkpoint/restart (SURVEY.md section 8 f) ----------------------------- */
+/* Asynchronous snapshot of the positions (original order) into host_xyz (pinned memory for a truly asynchronous
+ * copy): what FluidRenderWidget::updateParticleData uploads per particleChanged (Source/FluidRenderWidget.cpp:204-221).
+ * The solver may keep stepping; host_xyz is valid after sf_snapshot_wait. */
+int sf_snapshot_positions_async(sf_solver* s, float* host_xyz);
+int sf_snapshot_wait(sf_solver* s);
+/* {params, wall particles, simulated time, positions, velocities}; a restarted run continues bit-identically. */
+int sf_checkpoint_write(sf_solver* s, const char* path, float sim_time);
+int sf_checkpoint_read(const char* path, int device, sf_solver** out, float* sim_time);
+
 /* ---- parity / inspection fields (state of the LAST substep, original particle order) -------- */
 typedef enum sf_field {
     SF_FIELD_DENSITY = 0,        /* float[n]      rho after computeDensity (A.8) */

@@ -26,6 +26,7 @@ EXPORTS = [
     "sf_profile_enable", "sf_profile_reset", "sf_profile_get", "sf_launch_count", "sf_timer_start", "sf_timer_stop",
     "sf_comm_unique_id", "sf_comm_init", "sf_upload_particles_global", "sf_slab_info", "sf_download_owned",
     "sf_slab_plan", "sf_slab_rebalance", "sf_cell_layers", "sf_download_local", "sf_upload_local",
+    "sf_snapshot_positions_async", "sf_snapshot_wait", "sf_checkpoint_write", "sf_checkpoint_read",
 ]
 
 
@@ -103,6 +104,8 @@ def library():
         "sf_slab_info": [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(u32), C.POINTER(u32)],
         "sf_download_owned": [vp, vp, vp, vp, u32, C.POINTER(u32)],
         "sf_download_local": [vp, vp, vp, vp, u32, C.POINTER(u32)], "sf_upload_local": [vp, vp, vp, vp, u32],
+        "sf_snapshot_positions_async": [vp, vp], "sf_snapshot_wait": [vp],
+        "sf_checkpoint_write": [vp, C.c_char_p, f32], "sf_checkpoint_read": [C.c_char_p, C.c_int, C.POINTER(vp), C.POINTER(f32)],
         "sf_slab_plan": [vp, i32, i32, vp], "sf_slab_rebalance": [vp, i32, i32, vp], "sf_cell_layers": [PP, vp, u32, vp],
     }
     for name, argtypes in sig.items():
@@ -343,6 +346,29 @@ class SPHSolver:
 
     def neighbors(self):
         return self.field(FIELD_NEIGHBOR_COUNT), self.field(FIELD_NEIGHBOR_IDS)
+
+    # -- renderer hand-off / checkpoint
+    def snapshotPositionsAsync(self, host_xyz):
+        self._ck(self.L.sf_snapshot_positions_async(self.h, _ptr(host_xyz)))
+
+    def snapshotWait(self):
+        self._ck(self.L.sf_snapshot_wait(self.h))
+
+    def checkpointWrite(self, path, sim_time=0.0):
+        self._ck(self.L.sf_checkpoint_write(self.h, str(path).encode(), sim_time))
+
+    @classmethod
+    def fromCheckpoint(cls, path, device=0):
+        L = library()
+        h, t = C.c_void_p(), C.c_float(0)
+        rc = L.sf_checkpoint_read(str(path).encode(), device, C.byref(h), C.byref(t))
+        if rc:
+            raise SFError(rc, (L.sf_last_error(None) or b"").decode())
+        self = cls.__new__(cls)
+        self.L, self.h = L, h
+        self.params = SFParams()
+        L.sf_get_params(h, C.byref(self.params))
+        return self, t.value
 
     # -- multi-GPU (z-slabs; one SPHSolver per rank / GPU)
     def commInit(self, rank, nranks, unique_id_bytes):

@@ -55,6 +55,10 @@ struct sf_solver {
     std::vector<float> walls[6];
     bool         wallsSet = false;
     uint32_t     bndStride = 0;
+    cudaStream_t snapStream = nullptr; // asynchronous position snapshots for the viewer
+    cudaEvent_t  snapReady = nullptr, snapDone = nullptr;
+    float*       snapBuf = nullptr;
+    uint32_t     snapCap = 0;
     float*       stage = nullptr; // device staging for host<->device marshalling (2 x 12 B x cap)
     size_t       stageBytes = 0;
     DevState*    hostState = nullptr; // pinned
@@ -342,12 +346,12 @@ int enqueue_substep(sf_solver* s)
         }
         {
             LaunchScope ls(s, K_FORCE);
-            k_force_brick<<<std::min<uint32_t>(pairGrid, s->numSMs * s->occForce), kBrickThreads, kSmemPair, st>>>(B, P);
+            k_force_brick<<<std::min<uint32_t>(pairGrid, s->numSMs * s->occForce), kPairThreads, kSmemPair, st>>>(B, P);
         }
     }
     if(!slab) {
         LaunchScope ls(s, K_VISC_INTEGRATE);
-        k_visc_brick<<<std::min<uint32_t>(pairGrid, s->numSMs * s->occVisc), kBrickThreads, kSmemPair, st>>>(B, P, 0);
+        k_visc_brick<<<std::min<uint32_t>(pairGrid, s->numSMs * s->occVisc), kPairThreads, kSmemPair, st>>>(B, P, 0);
         SF_CUDA(s, cudaGetLastError());
         return SF_OK;
     }
@@ -425,13 +429,13 @@ int slab_exchange(sf_solver* s, uint32_t n, uint32_t nSlots)
     if(extent) k_fill_u32<<<std::min<uint32_t>(cdiv(extent, 256), s->numSMs * 8), 256, 0, cs>>>(B.idA, extent, kInvalidId);
     if(n) {
         LaunchScope ls(s, K_VISC_INTEGRATE);
-        k_visc_brick<<<std::min<uint32_t>(pairGrid, s->numSMs * s->occVisc), kBrickThreads, kSmemPair, cs>>>(B, P, 1);
+        k_visc_brick<<<std::min<uint32_t>(pairGrid, s->numSMs * s->occVisc), kPairThreads, kSmemPair, cs>>>(B, P, 1);
     }
     SF_CUDA(s, cudaEventRecord(L.evEdge, cs));
     if(n) { // interior bricks: leave a few CTA slots free so that the pack / NCCL kernels can run beside them
         LaunchScope    ls(s, K_VISC_INTEGRATE);
         const uint32_t g = std::min<uint32_t>(pairGrid, s->numSMs * s->occVisc);
-        k_visc_brick<<<g > 32 ? g - 16 : g, kBrickThreads, kSmemPair, cs>>>(B, P, 2);
+        k_visc_brick<<<g > 32 ? g - 16 : g, kPairThreads, kSmemPair, cs>>>(B, P, 2);
     }
     // ---- communication stream
     const int hasLower = L.rank > 0, hasUpper = L.rank < L.nranks - 1;
@@ -571,8 +575,8 @@ int sf_create(const sf_params* p, int device, sf_solver** out)
     if(e == cudaSuccess) e = cudaFuncSetAttribute(k_force_brick, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemPair));
     if(e == cudaSuccess) e = cudaFuncSetAttribute(k_visc_brick, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemPair));
     if(e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->occDensity, k_density_brick, kBrickThreads, kSmemDensity);
-    if(e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->occForce, k_force_brick, kBrickThreads, kSmemPair);
-    if(e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->occVisc, k_visc_brick, kBrickThreads, kSmemPair);
+    if(e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->occForce, k_force_brick, kPairThreads, kSmemPair);
+    if(e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->occVisc, k_visc_brick, kPairThreads, kSmemPair);
     if(e != cudaSuccess) {
         const std::string msg = std::string("sf_create: ") + cudaGetErrorString(e);
         sf_destroy(s);
@@ -599,6 +603,13 @@ void sf_destroy(sf_solver* s)
     cudaFree(B.cellTab); cudaFree(B.rho); cudaFree(B.rho2); cudaFree(B.accel); cudaFree(B.nbrL); cudaFree(B.nbrCnt); cudaFree(B.brickFlag); cudaFree(B.brickList);
     cudaFree(B.tabW); cudaFree(B.tabG); cudaFree(B.bnd); cudaFree(B.radixCounts); cudaFree(B.radixTotals); cudaFree(B.state);
     cudaFree(s->stage);
+    if(s->snapStream) {
+        cudaStreamSynchronize(s->snapStream);
+        cudaStreamDestroy(s->snapStream);
+        cudaEventDestroy(s->snapReady);
+        cudaEventDestroy(s->snapDone);
+    }
+    cudaFree(s->snapBuf);
     {
         sf_solver::Slab& L = s->slab;
         if(L.on && L.steps && std::getenv("SF_SLAB_TRACE"))
@@ -1134,6 +1145,127 @@ int sf_timer_stop(sf_solver* s, float* ms_out)
     SF_CUDA(s, cudaEventRecord(s->timerB, s->stream));
     SF_CUDA(s, cudaEventSynchronize(s->timerB));
     SF_CUDA(s, cudaEventElapsedTime(ms_out, s->timerA, s->timerB));
+    return SF_OK;
+}
+
+// ---- renderer hand-off: asynchronous position snapshot -------------------
+// FluidRenderWidget::updateParticleData uploads the "Position" array once per particleChanged signal
+// (Source/FluidRenderWidget.cpp:204-221).  The snapshot is scattered to original order on the compute stream,
+// copied to the (ideally pinned) host buffer on a separate copy stream, and the solver keeps stepping meanwhile.
+int sf_snapshot_positions_async(sf_solver* s, float* host_xyz)
+{
+    if(!s || !host_xyz) return SF_ERR_INVALID;
+    if(!s->uploaded) return fail(s, SF_ERR_INVALID, "no particles uploaded");
+    if(s->slab.on) return fail(s, SF_ERR_INVALID, "slab mode: use sf_download_owned");
+    SF_CUDA(s, cudaSetDevice(s->device));
+    if(!s->snapStream) {
+        SF_CUDA(s, cudaStreamCreateWithFlags(&s->snapStream, cudaStreamNonBlocking));
+        SF_CUDA(s, cudaEventCreateWithFlags(&s->snapReady, cudaEventDisableTiming));
+        SF_CUDA(s, cudaEventCreateWithFlags(&s->snapDone, cudaEventDisableTiming));
+    }
+    if(s->snapCap < s->n || !s->snapBuf) {
+        SF_CUDA(s, cudaStreamSynchronize(s->snapStream));
+        SF_CUDA(s, dev_alloc(s->snapBuf, static_cast<size_t>(s->npad) * 3));
+        s->snapCap = s->npad;
+    }
+    if(s->n) {
+        SF_CUDA(s, cudaStreamWaitEvent(s->stream, s->snapDone, 0)); // previous snapshot has left the buffer
+        {
+            LaunchScope ls(s, K_MARSHAL);
+            k_unpack_xyz<<<cdiv(s->n, 256), 256, 0, s->stream>>>(s->B.posA, s->B.idA, s->snapBuf, s->n);
+        }
+        SF_CUDA(s, cudaEventRecord(s->snapReady, s->stream));
+        SF_CUDA(s, cudaStreamWaitEvent(s->snapStream, s->snapReady, 0));
+        SF_CUDA(s, cudaMemcpyAsync(host_xyz, s->snapBuf, static_cast<size_t>(s->n) * 12, cudaMemcpyDeviceToHost, s->snapStream));
+    }
+    SF_CUDA(s, cudaEventRecord(s->snapDone, s->snapStream));
+    return SF_OK;
+}
+
+int sf_snapshot_wait(sf_solver* s)
+{
+    if(!s) return SF_ERR_INVALID;
+    if(!s->snapStream) return SF_OK;
+    SF_CUDA(s, cudaSetDevice(s->device));
+    SF_CUDA(s, cudaEventSynchronize(s->snapDone));
+    return SF_OK;
+}
+
+// ---- checkpoint / restart ------------------------------------------------
+// State = {params, wall particle sets, simulated time, positions, velocities in original order}.  Restarting
+// from it continues bit-identically: dt is recomputed from max |v|^2 (an exact max), and the sort re-derives
+// the cell order from positions and ids alone.
+namespace
+{
+struct CheckpointHeader {
+    char     magic[8]; // "SFCKPT1\0"
+    uint32_t paramsBytes, n, wallCount[6];
+    float    simTime;
+};
+} // namespace
+
+int sf_checkpoint_write(sf_solver* s, const char* path, float sim_time)
+{
+    if(!s || !path) return SF_ERR_INVALID;
+    if(!s->uploaded) return fail(s, SF_ERR_INVALID, "no particles uploaded");
+    if(s->slab.on) return fail(s, SF_ERR_INVALID, "checkpointing a slab run: gather with sf_download_owned");
+    const uint32_t     n = s->n;
+    std::vector<float> x(static_cast<size_t>(n) * 3), v(static_cast<size_t>(n) * 3);
+    int                rc = sf_download_positions(s, x.data());
+    if(rc) return rc;
+    rc = sf_download_velocities(s, v.data());
+    if(rc) return rc;
+    CheckpointHeader h{};
+    std::memcpy(h.magic, "SFCKPT1", 8);
+    h.paramsBytes = sizeof(sf_params);
+    h.n           = n;
+    h.simTime     = sim_time;
+    for(int w = 0; w < 6; ++w) h.wallCount[w] = static_cast<uint32_t>(s->walls[w].size() / 3);
+    FILE* f = std::fopen(path, "wb");
+    if(!f) return fail(s, SF_ERR_INVALID, std::string("cannot open ") + path);
+    bool ok = std::fwrite(&h, sizeof(h), 1, f) == 1 && std::fwrite(&s->params, sizeof(sf_params), 1, f) == 1;
+    for(int w = 0; w < 6 && ok; ++w)
+        if(h.wallCount[w]) ok = std::fwrite(s->walls[w].data(), 12, h.wallCount[w], f) == h.wallCount[w];
+    if(ok && n) ok = std::fwrite(x.data(), 12, n, f) == n && std::fwrite(v.data(), 12, n, f) == n;
+    std::fclose(f);
+    return ok ? SF_OK : fail(s, SF_ERR_INVALID, std::string("short write to ") + path);
+}
+
+int sf_checkpoint_read(const char* path, int device, sf_solver** out, float* sim_time)
+{
+    if(!path || !out) return fail(nullptr, SF_ERR_INVALID, "null argument");
+    *out    = nullptr;
+    FILE* f = std::fopen(path, "rb");
+    if(!f) return fail(nullptr, SF_ERR_INVALID, std::string("cannot open ") + path);
+    CheckpointHeader h{};
+    sf_params        p{};
+    bool ok = std::fread(&h, sizeof(h), 1, f) == 1 && std::memcmp(h.magic, "SFCKPT1", 8) == 0 && h.paramsBytes == sizeof(sf_params) &&
+              std::fread(&p, sizeof(p), 1, f) == 1;
+    std::vector<float> walls[6], x, v;
+    for(int w = 0; w < 6 && ok; ++w) {
+        walls[w].resize(static_cast<size_t>(h.wallCount[w]) * 3);
+        if(h.wallCount[w]) ok = std::fread(walls[w].data(), 12, h.wallCount[w], f) == h.wallCount[w];
+    }
+    if(ok) {
+        x.resize(static_cast<size_t>(h.n) * 3);
+        v.resize(static_cast<size_t>(h.n) * 3);
+        if(h.n) ok = std::fread(x.data(), 12, h.n, f) == h.n && std::fread(v.data(), 12, h.n, f) == h.n;
+    }
+    std::fclose(f);
+    if(!ok) return fail(nullptr, SF_ERR_INVALID, std::string("not a valid checkpoint: ") + path);
+    sf_solver* s  = nullptr;
+    int        rc = sf_create(&p, device, &s);
+    if(rc) return rc;
+    for(int w = 0; w < 6 && !rc; ++w) rc = sf_set_boundary_particles(s, w, walls[w].data(), h.wallCount[w]);
+    if(!rc) rc = sf_upload_particles(s, x.data(), v.data(), h.n);
+    if(!rc) rc = sf_make_ready(s);
+    if(rc) {
+        g_createError = s->lastError;
+        sf_destroy(s);
+        return rc;
+    }
+    if(sim_time) *sim_time = h.simTime;
+    *out = s;
     return SF_OK;
 }
 

@@ -285,3 +285,47 @@ def test_full_size_properties_double_dambreak_8m(sf):
             assert x.min() >= -1 + r and x.max() <= 1 - r and np.isfinite(x).all()
         gpu.close()
     assert exact(outs[0][0], outs[1][0]) and exact(outs[0][1], outs[1][1])
+
+
+def test_checkpoint_restart_continues_bit_identically(sf, tmp_path):
+    """{params, walls, positions, velocities, time} is the whole state."""
+    p = sf.default_params(24, "DoubleDambreak", viscosity=0.08)
+    pos = sf.scene_generate(p)
+    a = sf.SPHSolver(p)
+    a.setParticles(pos)
+    a.generateBoundaryParticles(5)
+    a.makeReady()
+    t = a.advanceSteps(60, want_time=True)
+    ck = tmp_path / "state.sfck"
+    a.checkpointWrite(ck, t)
+    b, tb = sf.SPHSolver.fromCheckpoint(ck)
+    assert np.float32(tb) == np.float32(t) and b.getNumParticles() == len(pos)
+    assert abs(b.params.viscosity - 0.08) < 1e-7
+    for w in range(6):
+        assert exact(a.getBoundaryParticles(w), b.getBoundaryParticles(w))
+    for _ in range(40):
+        assert a.advanceFrame() == b.advanceFrame()
+    assert exact(a.getParticles(), b.getParticles()) and exact(a.getVelocity(), b.getVelocity())
+    a.close()
+    b.close()
+    with pytest.raises(sf.SFError):
+        sf.SPHSolver.fromCheckpoint(tmp_path / "missing.sfck")
+
+
+def test_async_position_snapshot(sf):
+    """the viewer's position buffer is filled while the solver keeps stepping."""
+    import torch
+    p = sf.default_params(32, "Dambreak")
+    pos = sf.scene_generate(p)
+    g = sf.SPHSolver(p)
+    g.setParticles(pos)
+    g.makeReady()
+    host = torch.empty((len(pos), 3), dtype=torch.float32).pin_memory()
+    g.advanceSteps(10)
+    expect = g.getParticles()
+    g.snapshotPositionsAsync(host)
+    g.advanceSteps(10)  # keeps running while the copy is in flight
+    g.snapshotWait()
+    assert exact(host.numpy(), expect)
+    assert not exact(g.getParticles(), expect)
+    g.close()
