@@ -346,12 +346,12 @@ int enqueue_substep(sf_solver* s)
         }
         {
             LaunchScope ls(s, K_FORCE);
-            k_force_brick<<<std::min<uint32_t>(pairGrid, s->numSMs * s->occForce), kPairThreads, kSmemPair, st>>>(B, P);
+            k_force_brick<<<std::min<uint32_t>(pairGrid, s->numSMs * s->occForce), kBrickThreads, kSmemPair, st>>>(B, P);
         }
     }
     if(!slab) {
         LaunchScope ls(s, K_VISC_INTEGRATE);
-        k_visc_brick<<<std::min<uint32_t>(pairGrid, s->numSMs * s->occVisc), kPairThreads, kSmemPair, st>>>(B, P, 0);
+        k_visc_brick<<<std::min<uint32_t>(pairGrid, s->numSMs * s->occVisc), kBrickThreads, kSmemPair, st>>>(B, P, 0);
         SF_CUDA(s, cudaGetLastError());
         return SF_OK;
     }
@@ -429,13 +429,13 @@ int slab_exchange(sf_solver* s, uint32_t n, uint32_t nSlots)
     if(extent) k_fill_u32<<<std::min<uint32_t>(cdiv(extent, 256), s->numSMs * 8), 256, 0, cs>>>(B.idA, extent, kInvalidId);
     if(n) {
         LaunchScope ls(s, K_VISC_INTEGRATE);
-        k_visc_brick<<<std::min<uint32_t>(pairGrid, s->numSMs * s->occVisc), kPairThreads, kSmemPair, cs>>>(B, P, 1);
+        k_visc_brick<<<std::min<uint32_t>(pairGrid, s->numSMs * s->occVisc), kBrickThreads, kSmemPair, cs>>>(B, P, 1);
     }
     SF_CUDA(s, cudaEventRecord(L.evEdge, cs));
     if(n) { // interior bricks: leave a few CTA slots free so that the pack / NCCL kernels can run beside them
         LaunchScope    ls(s, K_VISC_INTEGRATE);
         const uint32_t g = std::min<uint32_t>(pairGrid, s->numSMs * s->occVisc);
-        k_visc_brick<<<g > 32 ? g - 16 : g, kPairThreads, kSmemPair, cs>>>(B, P, 2);
+        k_visc_brick<<<g > 32 ? g - 4 : g, kBrickThreads, kSmemPair, cs>>>(B, P, 2);
     }
     // ---- communication stream
     const int hasLower = L.rank > 0, hasUpper = L.rank < L.nranks - 1;
@@ -575,8 +575,8 @@ int sf_create(const sf_params* p, int device, sf_solver** out)
     if(e == cudaSuccess) e = cudaFuncSetAttribute(k_force_brick, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemPair));
     if(e == cudaSuccess) e = cudaFuncSetAttribute(k_visc_brick, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemPair));
     if(e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->occDensity, k_density_brick, kBrickThreads, kSmemDensity);
-    if(e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->occForce, k_force_brick, kPairThreads, kSmemPair);
-    if(e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->occVisc, k_visc_brick, kPairThreads, kSmemPair);
+    if(e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->occForce, k_force_brick, kBrickThreads, kSmemPair);
+    if(e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->occVisc, k_visc_brick, kBrickThreads, kSmemPair);
     if(e != cudaSuccess) {
         const std::string msg = std::string("sf_create: ") + cudaGetErrorString(e);
         sf_destroy(s);
