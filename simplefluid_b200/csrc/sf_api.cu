@@ -67,6 +67,9 @@ struct sf_solver {
     int          occDensity = 1, occForce = 1, occVisc = 1;
     uint32_t     numBricks = 0, brickCap = 0;
     uint32_t     nSlots = 0; // live + dead slots of the A arrays (== n on a single GPU)
+    cudaGraphExec_t stepGraph = nullptr; // captured substep (single GPU); dropped whenever the launch arguments change
+    uint64_t        graphLaunches = 0;
+    bool            useGraph = true;
     int          axisS = 2;  // slow axis of the cell key: 2 = z (reference order), 1 = y (slab runs that are longer in y)
     int32_t      nS() const { return grid[axisS]; }
     int32_t      nM() const { return grid[3 - axisS]; }
@@ -103,6 +106,14 @@ struct sf_solver {
 
 namespace
 {
+void drop_graph(sf_solver* s)
+{
+    if(s->stepGraph) {
+        cudaGraphExecDestroy(s->stepGraph);
+        s->stepGraph = nullptr;
+    }
+}
+
 int fail(sf_solver* s, int code, const std::string& msg)
 {
     if(s) s->lastError = msg;
@@ -265,7 +276,7 @@ int slab_exchange(sf_solver* s, uint32_t n, uint32_t nSlots);
 
 // One reference substep (advanceFrame, EXE@0x140016810) as a launch sequence on the solver's stream.
 // n = live particles, nSlots >= n = slots of the A arrays to sort (slab mode keeps last step's dead ghost slots).
-int enqueue_substep(sf_solver* s)
+int enqueue_substep_launches(sf_solver* s)
 {
     DevBuffers&     B  = s->B;
     const DevParams P  = s->P;
@@ -356,6 +367,34 @@ int enqueue_substep(sf_solver* s)
         return SF_OK;
     }
     return slab_exchange(s, n, nSlots);
+}
+
+// Single-GPU substeps are replayed from a CUDA graph (the launch sequence and every kernel argument are fixed
+// between two makeReady calls; dt and the work cursors live in device memory), which removes the launch gaps that
+// dominate small scenes.  Profiling and slab mode use direct launches.
+int enqueue_substep(sf_solver* s)
+{
+    if(s->slab.on || s->profiling || !s->useGraph || s->n == 0) return enqueue_substep_launches(s);
+    if(!s->stepGraph) {
+        const uint64_t before = s->launches;
+        cudaGraph_t    graph  = nullptr;
+        SF_CUDA(s, cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = enqueue_substep_launches(s);
+        cudaError_t e = cudaStreamEndCapture(s->stream, &graph);
+        if(rc) {
+            if(graph) cudaGraphDestroy(graph);
+            return rc;
+        }
+        SF_CUDA(s, e);
+        e = cudaGraphInstantiate(&s->stepGraph, graph, 0);
+        cudaGraphDestroy(graph);
+        SF_CUDA(s, e);
+        s->graphLaunches = s->launches - before;
+        s->launches      = before;
+    }
+    SF_CUDA(s, cudaGraphLaunch(s->stepGraph, s->stream));
+    s->launches += s->graphLaunches;
+    return SF_OK;
 }
 
 int read_state(sf_solver* s)
@@ -583,6 +622,7 @@ int sf_create(const sf_params* p, int device, sf_solver** out)
         return fail(nullptr, SF_ERR_CUDA, msg);
     }
     s->stream = s->ownStream;
+    s->useGraph = std::getenv("SF_NO_GRAPH") == nullptr;
     s->occDensity = std::max(s->occDensity, 1);
     s->occForce   = std::max(s->occForce, 1);
     s->occVisc    = std::max(s->occVisc, 1);
@@ -595,6 +635,7 @@ void sf_destroy(sf_solver* s)
     if(!s) return;
     cudaSetDevice(s->device);
     if(s->stream) cudaStreamSynchronize(s->stream);
+    drop_graph(s);
     fold_pending(s);
     for(auto e : s->eventPool) cudaEventDestroy(e);
     DevBuffers& B = s->B;
@@ -653,6 +694,7 @@ int sf_set_stream(sf_solver* s, void* cuda_stream)
     cudaSetDevice(s->device);
     cudaStreamSynchronize(s->stream);
     s->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : s->ownStream;
+    drop_graph(s);
     return SF_OK;
 }
 
@@ -802,6 +844,7 @@ int sf_make_ready(sf_solver* s)
     }
     fill_dev_params(s);
     if(s->slab.on) slab_configure_window(s);
+    drop_graph(s);
     // device state: step 0, both max-velocity slots at FLT_MIN, then computeMaxVel of the upload
     DevState init{};
     init.maxv2Bits[0] = init.maxv2Bits[1] = 0x00800000u; // FLT_MIN
@@ -952,6 +995,7 @@ int sf_set_capture(sf_solver* s, int on)
     if(!s) return SF_ERR_INVALID;
     s->capture   = on != 0;
     s->P.capture = on ? 1 : 0;
+    drop_graph(s);
     return SF_OK;
 }
 
