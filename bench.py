@@ -324,10 +324,17 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_b200(args)
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_b200(args)
+    except BaseException:
+        # a failing rank must not sit in NCCL / torch teardown while the others wait in a collective
+        import traceback
+        traceback.print_exc()
+        sys.stderr.flush()
+        os._exit(1)
     try:
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized():

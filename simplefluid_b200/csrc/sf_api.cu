@@ -83,7 +83,8 @@ struct sf_solver {
         cudaStream_t         commStream = nullptr;
         cudaEvent_t          evEdge = nullptr, evExchanged = nullptr;
         float4 *             sendLo = nullptr, *sendHi = nullptr, *recvLo = nullptr, *recvHi = nullptr;
-        uint32_t             xcap = 0;
+        uint32_t             sendCap = 0, recvCap = 0;
+        uint64_t             regrowths = 0;
         uint32_t *           layerStart = nullptr, *counters = nullptr, *row = nullptr, *table = nullptr;
         uint32_t*            hostTable = nullptr; // pinned
         uint64_t             nGlobal = 0;
@@ -242,16 +243,36 @@ void fill_dev_params(sf_solver* s)
     P.bndStride = s->bndStride;
 }
 
-int ensure_particle_capacity(sf_solver* s, uint32_t n)
+// preserve > 0: the first `preserve` slots of the state arrays (posA / velA / idA) survive the reallocation; every
+// other per-particle array is scratch that the next substep rewrites.  The caller has synchronised the streams.
+template<class T>
+cudaError_t dev_grow(T*& p, size_t newCount, size_t preserve)
+{
+    T*          q = nullptr;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&q), newCount * sizeof(T));
+    if(e != cudaSuccess) return e;
+    if(p && preserve) e = cudaMemcpy(q, p, preserve * sizeof(T), cudaMemcpyDeviceToDevice);
+    if(p) cudaFree(p);
+    p = q;
+    return e;
+}
+
+int ensure_particle_capacity(sf_solver* s, uint32_t n, uint32_t preserve = 0)
 {
     if(n <= s->cap && s->B.posA) return SF_OK;
     const uint32_t cap  = n;
     const uint32_t npad = (cap + 127u) & ~127u;
-    SF_CUDA(s, dev_alloc(s->B.posA, npad));
-    SF_CUDA(s, dev_alloc(s->B.velA, npad));
+    if(preserve) {
+        SF_CUDA(s, dev_grow(s->B.posA, npad, preserve));
+        SF_CUDA(s, dev_grow(s->B.velA, npad, preserve));
+        SF_CUDA(s, dev_grow(s->B.idA, npad, preserve));
+    } else {
+        SF_CUDA(s, dev_alloc(s->B.posA, npad));
+        SF_CUDA(s, dev_alloc(s->B.velA, npad));
+        SF_CUDA(s, dev_alloc(s->B.idA, npad));
+    }
     SF_CUDA(s, dev_alloc(s->B.posB, npad));
     SF_CUDA(s, dev_alloc(s->B.velB, npad));
-    SF_CUDA(s, dev_alloc(s->B.idA, npad));
     SF_CUDA(s, dev_alloc(s->B.idB, npad));
     for(int i = 0; i < 2; ++i) {
         SF_CUDA(s, dev_alloc(s->B.keys[i], npad));
@@ -481,7 +502,7 @@ int slab_exchange(sf_solver* s, uint32_t n, uint32_t nSlots)
     SF_CUDA(s, cudaStreamWaitEvent(ms, L.evEdge, 0));
     SF_CUDA(s, cudaMemsetAsync(L.counters, 0, 2 * sizeof(uint32_t), ms));
     if(n) k_slab_pack<<<std::min<uint32_t>(cdiv(n, 256), 64), 256, 0, ms>>>(B.posA, B.velA, B.idA, L.layerStart, P, L.next[L.rank], L.next[L.rank + 1],
-                                                                               hasLower, hasUpper, L.sendLo, L.sendHi, L.xcap, L.counters);
+                                                                               hasLower, hasUpper, L.sendLo, L.sendHi, L.sendCap, L.counters);
     k_slab_row<<<1, 1, 0, ms>>>(L.layerStart, L.counters, P, L.row);
     if(nc.AllGather(L.row, L.table, kRowWords, ncclUint32, L.comm, ms) != ncclSuccess) return fail(s, SF_ERR_COMM, "ncclAllGather failed");
     SF_CUDA(s, cudaMemcpyAsync(L.hostTable, L.table, sizeof(uint32_t) * kRowWords * L.nranks, cudaMemcpyDeviceToHost, ms));
@@ -493,9 +514,31 @@ int slab_exchange(sf_solver* s, uint32_t n, uint32_t nSlots)
     const uint32_t  sendLo = T[L.rank * kRowWords + 0], sendHi = T[L.rank * kRowWords + 1], nOwn = T[L.rank * kRowWords + 2];
     const uint32_t  recvLo = hasLower ? T[(L.rank - 1) * kRowWords + 1] : 0u;
     const uint32_t  recvHi = hasUpper ? T[(L.rank + 1) * kRowWords + 0] : 0u;
-    for(int r = 0; r < L.nranks; ++r)
-        if(T[r * kRowWords] > L.xcap || T[r * kRowWords + 1] > L.xcap) return fail(s, SF_ERR_STATE, "slab exchange buffer too small (load imbalance beyond the reserved capacity)");
-    if(static_cast<uint64_t>(n) + recvLo + recvHi > s->cap) return fail(s, SF_ERR_STATE, "slab particle capacity exceeded");
+    // Capacities follow the load (a settling flow can concentrate in few slabs): everything below is rank-local.
+    if(std::max(sendLo, sendHi) > L.sendCap) { // the pack kernel dropped the overflow: grow and pack again (same counts)
+        L.sendCap = std::max(sendLo, sendHi) + std::max(sendLo, sendHi) / 4 + 4096u;
+        SF_CUDA(s, dev_alloc(L.sendLo, static_cast<size_t>(L.sendCap) * 2));
+        SF_CUDA(s, dev_alloc(L.sendHi, static_cast<size_t>(L.sendCap) * 2));
+        SF_CUDA(s, cudaMemsetAsync(L.counters, 0, 2 * sizeof(uint32_t), ms));
+        k_slab_pack<<<std::min<uint32_t>(cdiv(n, 256), 64), 256, 0, ms>>>(B.posA, B.velA, B.idA, L.layerStart, P, L.next[L.rank], L.next[L.rank + 1],
+                                                                            hasLower, hasUpper, L.sendLo, L.sendHi, L.sendCap, L.counters);
+        L.regrowths++;
+    }
+    if(std::max(recvLo, recvHi) > L.recvCap) {
+        L.recvCap = std::max(recvLo, recvHi) + std::max(recvLo, recvHi) / 4 + 4096u;
+        SF_CUDA(s, dev_alloc(L.recvLo, static_cast<size_t>(L.recvCap) * 2));
+        SF_CUDA(s, dev_alloc(L.recvHi, static_cast<size_t>(L.recvCap) * 2));
+        L.regrowths++;
+    }
+    if(static_cast<uint64_t>(n) + recvLo + recvHi > s->cap) {
+        SF_CUDA(s, cudaStreamSynchronize(cs)); // the interior bricks still write the state arrays
+        SF_CUDA(s, cudaStreamSynchronize(ms)); // a re-run pack kernel may still read them
+        const uint64_t want = static_cast<uint64_t>(n) + recvLo + recvHi;
+        if(want + want / 2 > 0xfffffff0ull) return fail(s, SF_ERR_OOM, "more than 2^32 particle slots on one rank");
+        const int rc = ensure_particle_capacity(s, static_cast<uint32_t>(want + want / 2), n);
+        if(rc) return rc;
+        L.regrowths++;
+    }
     if(nc.GroupStart() != ncclSuccess) return fail(s, SF_ERR_COMM, "ncclGroupStart failed");
     ncclResult_t r = ncclSuccess;
     if(hasLower) {
@@ -654,8 +697,9 @@ void sf_destroy(sf_solver* s)
     {
         sf_solver::Slab& L = s->slab;
         if(L.on && L.steps && std::getenv("SF_SLAB_TRACE"))
-            std::fprintf(stderr, "[sf slab rank %d] %llu substeps: host wait for edge+pack+allgather %.3f ms/step, post exchange %.3f ms/step, exchanged %.1f particles/step\n",
-                         L.rank, (unsigned long long)L.steps, L.tWaitPack / L.steps * 1e3, L.tPost / L.steps * 1e3, double(L.exchangedParticles) / L.steps);
+            std::fprintf(stderr, "[sf slab rank %d] %llu substeps: host wait for edge+pack+allgather %.3f ms/step, post exchange %.3f ms/step, exchanged %.1f particles/step, %llu capacity regrowths, axis %c\n",
+                         L.rank, (unsigned long long)L.steps, L.tWaitPack / L.steps * 1e3, L.tPost / L.steps * 1e3, double(L.exchangedParticles) / L.steps,
+                         (unsigned long long)L.regrowths, s->axisS == 1 ? 'y' : 'z');
         if(L.comm && nccl_api().CommDestroy) nccl_api().CommDestroy(L.comm);
         cudaFree(L.sendLo); cudaFree(L.sendHi); cudaFree(L.recvLo); cudaFree(L.recvHi);
         cudaFree(L.layerStart); cudaFree(L.counters); cudaFree(L.row); cudaFree(L.table);
@@ -1371,11 +1415,12 @@ int sf_upload_particles_global(sf_solver* s, const float* pos_xyz, const float* 
         histY[c[1]]++;
         histZ[c[2]]++;
     }
-    // slab axis = the slow axis (y or z) along which the particle set spans more cell layers: thicker slabs, so the
-    // 3 + 3 ghost layers weigh less.  Every rank sees the same input and takes the same decision.
+    // slab axis: z (orthogonal to gravity, so a settling flow keeps spanning it) unless the particle set spans at
+    // least twice as many cell layers in y: thicker slabs, so the 3 + 3 ghost layers weigh less (64 M dambreak: 283 y
+    // layers against 101 z layers).  Every rank sees the same input and takes the same decision.
     auto occupied = [](const std::vector<uint64_t>& h) { size_t k = 0; for(uint64_t v : h) k += v ? 1 : 0; return k; };
     if(const char* force = std::getenv("SF_SLAB_AXIS")) s->axisS = (force[0] == 'y' || force[0] == 'Y' || force[0] == '1') ? 1 : 2;
-    else s->axisS = occupied(histY) > occupied(histZ) ? 1 : 2;
+    else s->axisS = occupied(histY) >= 2 * occupied(histZ) ? 1 : 2;
     const std::vector<uint64_t>& hist  = s->axisS == 1 ? histY : histZ;
     const std::vector<int32_t>&  layer = s->axisS == 1 ? layerY : layerZ;
     s->grid[0] = g[0]; s->grid[1] = g[1]; s->grid[2] = g[2];
@@ -1396,14 +1441,16 @@ int sf_upload_particles_global(sf_solver* s, const float* pos_xyz, const float* 
     }
     const uint32_t n = static_cast<uint32_t>(hid.size());
     // room for load-balance drift, ghosts and the dead slots of one substep
-    const uint32_t want = n + n / 2 + (1u << 18);
+    // SF_SLAB_TIGHT (tests): start with almost no headroom so that the on-demand growth paths are exercised
+    const bool     tight = std::getenv("SF_SLAB_TIGHT") != nullptr;
+    const uint32_t want  = tight ? n + 64u : n + n / 2 + (1u << 18);
     int rc = ensure_particle_capacity(s, want);
     if(rc) return rc;
-    L.xcap = std::max<uint32_t>(want / 4, 1u << 16);
-    SF_CUDA(s, dev_alloc(L.sendLo, static_cast<size_t>(L.xcap) * 2));
-    SF_CUDA(s, dev_alloc(L.sendHi, static_cast<size_t>(L.xcap) * 2));
-    SF_CUDA(s, dev_alloc(L.recvLo, static_cast<size_t>(L.xcap) * 2));
-    SF_CUDA(s, dev_alloc(L.recvHi, static_cast<size_t>(L.xcap) * 2));
+    L.sendCap = L.recvCap = tight ? 256u : std::max<uint32_t>(want / 4, 1u << 16);
+    SF_CUDA(s, dev_alloc(L.sendLo, static_cast<size_t>(L.sendCap) * 2));
+    SF_CUDA(s, dev_alloc(L.sendHi, static_cast<size_t>(L.sendCap) * 2));
+    SF_CUDA(s, dev_alloc(L.recvLo, static_cast<size_t>(L.recvCap) * 2));
+    SF_CUDA(s, dev_alloc(L.recvHi, static_cast<size_t>(L.recvCap) * 2));
     SF_CUDA(s, dev_alloc(L.layerStart, static_cast<size_t>(std::max(g[1], g[2])) + 2 * kGhost + 2));
     if(n) {
         float*    dpos = s->stage;

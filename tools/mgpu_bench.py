@@ -24,6 +24,15 @@ g = sf.SPHSolver(p, device=local)
 g.commInit(rank, world, uid[0])
 g.setParticlesGlobal(pos)
 g.makeReady()
+def _die(exc):
+    # never hang in NCCL / torch teardown while the other ranks wait in a collective
+    import traceback
+    traceback.print_exception(exc)
+    sys.stderr.flush()
+    os._exit(1)
+
+
+sys.excepthook = lambda t, e, tb: _die(e)
 g.advanceSteps(5)
 g.synchronize()
 dist.barrier()
