@@ -657,7 +657,7 @@ float sfo_advance_frame(sfo_solver* s)
 { /* EXE@0x140016810 (A.15) */
     if (!s->ready) sfo_make_ready(s);
 #ifdef _OPENMP
-    if (s->nthreads > 0) omp_set_num_threads(s->nthreads);
+    omp_set_num_threads(s->nthreads > 0 ? s->nthreads : omp_get_num_procs()); /* 0 = all host cores (TBB "automatic") */
 #endif
     double t0 = now_s();
     float dt = compute_time_step(s);
