@@ -945,6 +945,23 @@ int sf_advance_frame_time(sf_solver* s, double frame_time, float* time_out, uint
     if(rc) return rc;
     if(!(frame_time > 0.0)) return fail(s, SF_ERR_INVALID, "frame_time must be positive");
     SF_CUDA(s, cudaSetDevice(s->device));
+    if(s->slab.on) {
+        // slab substeps synchronise with the host anyway (exchange sizes), so the loop of Simulator.cpp:46-51 runs on
+        // the host; dt is identical on every rank (all-reduced max |v|^2), hence so is the number of substeps
+        float    frameTime = 0.f;
+        uint32_t k         = 0;
+        while(static_cast<double>(frameTime) < frame_time) {
+            rc = enqueue_substep(s);
+            if(rc) return rc;
+            rc = read_state(s);
+            if(rc) return rc;
+            frameTime = frameTime + s->hostState->dt;
+            ++k;
+        }
+        if(time_out) *time_out = frameTime;
+        if(nsteps_out) *nsteps_out = k;
+        return SF_OK;
+    }
     rc = read_state(s);
     if(rc) return rc;
     const unsigned long long steps0 = s->hostState->stepsDone;
@@ -990,6 +1007,7 @@ int sf_synchronize(sf_solver* s)
 int sf_step_host(sf_solver* s, float* pos_xyz, float* vel_xyz, uint32_t n, float* dt_out)
 {
     if(!s || !pos_xyz || !vel_xyz) return SF_ERR_INVALID;
+    if(s->slab.on) return fail(s, SF_ERR_INVALID, "slab mode: use sf_upload_local / sf_advance_frame / sf_download_local");
     const bool sameShape = s->uploaded && s->ready && n == s->n;
     int        rc;
     if(!sameShape) {
