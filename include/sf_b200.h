@@ -122,6 +122,11 @@ int sf_synchronize(sf_solver* s);
 /* Stateless host-buffer step (what bench.py's e2e leg times): upload pos/vel, one substep,
  * download pos/vel into the same buffers. */
 int sf_step_host(sf_solver* s, float* pos_xyz, float* vel_xyz, uint32_t n, float* dt_out);
+/* Page-locked host buffers for the calls above that take host pointers (sf_step_host, sf_upload_*, sf_download_*,
+ * sf_snapshot_positions_async): with them the copies run at full PCIe rate and beside the kernels; pageable
+ * memory works too, slower.  The reference keeps its arrays in std::vector (Include/QtSPHSolver.h:33-34). */
+int sf_host_alloc(uint64_t bytes, void** out);
+int sf_host_free(void* p);
 
 /* ---- renderer hand-off and checkpoint/restart (SURVEY.md section 8 f) ----------------------------- */
 /* Asynchronous snapshot of the positions (original order) into host_xyz (pinned memory for a truly asynchronous

@@ -10,10 +10,10 @@ There is no CPU fallback: importing works anywhere, but every compute call raise
 the library or a B200-class GPU is missing.
 """
 from .binding import (  # noqa: F401
-    SCENES, SFError, SFParams, SPHSolver, build_library, default_params, library, library_path, scene_generate,
+    PinnedArray, SCENES, SFError, SFParams, SPHSolver, build_library, default_params, library, library_path, scene_generate,
 )
 
 HAS_SLAB = True  # multi-GPU z-slab decomposition is built into the library
 
-__all__ = ["HAS_SLAB", "SCENES", "SFError", "SFParams", "SPHSolver", "build_library", "default_params", "library",
+__all__ = ["HAS_SLAB", "PinnedArray", "SCENES", "SFError", "SFParams", "SPHSolver", "build_library", "default_params", "library",
            "library_path", "scene_generate"]

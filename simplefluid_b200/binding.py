@@ -27,6 +27,7 @@ EXPORTS = [
     "sf_comm_unique_id", "sf_comm_init", "sf_upload_particles_global", "sf_slab_info", "sf_download_owned",
     "sf_slab_plan", "sf_slab_rebalance", "sf_cell_layers", "sf_download_local", "sf_upload_local",
     "sf_snapshot_positions_async", "sf_snapshot_wait", "sf_checkpoint_write", "sf_checkpoint_read",
+    "sf_host_alloc", "sf_host_free",
 ]
 
 
@@ -106,6 +107,7 @@ def library():
         "sf_download_local": [vp, vp, vp, vp, u32, C.POINTER(u32)], "sf_upload_local": [vp, vp, vp, vp, u32],
         "sf_snapshot_positions_async": [vp, vp], "sf_snapshot_wait": [vp],
         "sf_checkpoint_write": [vp, C.c_char_p, f32], "sf_checkpoint_read": [C.c_char_p, C.c_int, C.POINTER(vp), C.POINTER(f32)],
+        "sf_host_alloc": [u64, C.POINTER(vp)], "sf_host_free": [vp],
         "sf_slab_plan": [vp, i32, i32, vp], "sf_slab_rebalance": [vp, i32, i32, vp], "sf_cell_layers": [PP, vp, u32, vp],
     }
     for name, argtypes in sig.items():
@@ -118,6 +120,32 @@ def library():
     L.sf_last_error.restype = C.c_char_p
     _lib = L
     return L
+
+
+class PinnedArray:
+    """numpy view of a page-locked host buffer from sf_host_alloc (freed on close() / garbage collection)."""
+
+    def __init__(self, shape, dtype=np.float32):
+        self.L = library()
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self.ptr = C.c_void_p()
+        rc = self.L.sf_host_alloc(max(nbytes, 1), C.byref(self.ptr))
+        if rc:
+            raise SFError(rc, (self.L.sf_last_error(None) or b"").decode())
+        buf = (C.c_char * max(nbytes, 1)).from_address(self.ptr.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def close(self):
+        if self.ptr is not None and self.ptr.value:
+            self.array = None
+            self.L.sf_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def default_params(resolution=24.0, scene="Dambreak", **overrides):

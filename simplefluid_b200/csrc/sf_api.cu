@@ -24,11 +24,11 @@ thread_local std::string g_createError;
 
 enum KernelId {
     K_BEGIN = 0, K_HASH, K_RADIX_HIST, K_RADIX_SCAN, K_RADIX_SCATTER, K_CLEAR_CELLS, K_CELL_BOUNDS, K_BRICK_COMPACT, K_REORDER,
-    K_DENSITY, K_CORRECT_DENSITY, K_FORCE, K_VISC_INTEGRATE, K_MARSHAL, K_COUNT
+    K_DENSITY, K_CORRECT_DENSITY, K_FORCE, K_VISC_INTEGRATE, K_MARSHAL, K_HASH_COUNT, K_CELL_SCAN, K_COUNT_SCATTER, K_COUNT
 };
 const char* const kKernelNames[K_COUNT] = {
     "k_begin_step", "k_hash", "k_radix_hist", "k_radix_scan", "k_radix_scatter", "k_clear_cells", "k_cell_bounds", "k_brick_compact",
-    "k_reorder", "k_density", "k_correct_density", "k_force", "k_visc_integrate", "k_marshal"
+    "k_reorder", "k_density", "k_correct_density", "k_force", "k_visc_integrate", "k_marshal", "k_hash_count", "k_cell_scan", "k_count_scatter"
 };
 
 struct PendingEvent {
@@ -55,6 +55,8 @@ struct sf_solver {
     std::vector<float> walls[6];
     bool         wallsSet = false;
     uint32_t     bndStride = 0;
+    cudaStream_t xferStream = nullptr; // sf_step_host: host<->device copies beside the compute stream
+    cudaEvent_t  evPosUp = nullptr, evVelUp = nullptr, evPosOut = nullptr, evVelOut = nullptr;
     cudaStream_t snapStream = nullptr; // asynchronous position snapshots for the viewer
     cudaEvent_t  snapReady = nullptr, snapDone = nullptr;
     float*       snapBuf = nullptr;
@@ -63,6 +65,10 @@ struct sf_solver {
     size_t       stageBytes = 0;
     DevState*    hostState = nullptr; // pinned
     uint32_t     radixBlocks = 0;
+    int          densityH  = 0;          // SF_DENSITY=h / h2: half-precision candidate filter (k_density_brick_h<1> / <2>)
+    bool         countSort = false;      // SF_SORT=count: counting sort by cell instead of the radix passes
+    uint32_t*    cellTileSums = nullptr; // counting sort: per-tile particle counts of the cell table
+    uint64_t     cellTileCap = 0;
     int          sortPasses = 0, sortBits[4] = { 0, 0, 0, 0 };
     int          occDensity = 1, occForce = 1, occVisc = 1;
     uint32_t     numBricks = 0, brickCap = 0;
@@ -297,7 +303,9 @@ int slab_exchange(sf_solver* s, uint32_t n, uint32_t nSlots);
 
 // One reference substep (advanceFrame, EXE@0x140016810) as a launch sequence on the solver's stream.
 // n = live particles, nSlots >= n = slots of the A arrays to sort (slab mode keeps last step's dead ghost slots).
-int enqueue_substep_launches(sf_solver* s)
+// velHostXYZ != nullptr (sf_step_host): the velocities of this substep are still on their way from the host; they
+// are gathered from that xyz array (after evVelUp) between the density and the force pass, dt follows them.
+int enqueue_substep_launches(sf_solver* s, const float* velHostXYZ = nullptr)
 {
     DevBuffers&     B  = s->B;
     const DevParams P  = s->P;
@@ -313,48 +321,75 @@ int enqueue_substep_launches(sf_solver* s)
     }
     {
         LaunchScope ls(s, K_BEGIN);
-        k_begin_step<<<1, 1, 0, st>>>(B.state, P);
+        k_begin_step<<<1, 1, 0, st>>>(B.state, P, velHostXYZ ? kBeginResets : kBeginAll);
     }
     if(nSlots == 0 && !slab) {
+        if(velHostXYZ) k_begin_step<<<1, 1, 0, st>>>(B.state, P, kBeginClock);
         SF_CUDA(s, cudaGetLastError());
         return SF_OK;
     }
     int cur = 0;
-    if(nSlots) {
+    if(s->countSort) {
+        // counting sort by cell (sf_kernels.cuh, section 1'): cell table first, then the slot permutation
         {
-            LaunchScope ls(s, K_HASH);
-            k_hash<<<cdiv(nSlots, 256), 256, 0, st>>>(B.posA, B.idA, B.keys[0], B.vals[0], nSlots, P, B.state);
+            LaunchScope  ls(s, K_CLEAR_CELLS);
+            const size_t nvec = (s->ncells * sizeof(uint2) + 15) / 16;
+            k_clear_cells<<<std::min<uint32_t>(cdiv(nvec, 256), s->numSMs * 16), 256, 0, st>>>(reinterpret_cast<uint4*>(B.cellTab), nvec, B.state);
         }
-        const uint32_t nb    = cdiv(nSlots, RS_TILE);
-        int            shift = 0;
-        for(int pass = 0; pass < s->sortPasses; ++pass) {
-            const int radix = 1 << s->sortBits[pass];
-            {
-                LaunchScope ls(s, K_RADIX_HIST);
-                k_radix_hist<<<nb, RS_THREADS, 0, st>>>(B.keys[cur], nSlots, shift, radix, B.radixCounts, nb, B.state);
-            }
-            {
-                LaunchScope ls(s, K_RADIX_SCAN);
-                k_radix_scan<<<radix, 1024, 0, st>>>(B.radixCounts, nb, B.radixTotals, B.state);
-            }
-            {
-                LaunchScope ls(s, K_RADIX_SCATTER);
-                k_radix_scatter<<<nb, RS_THREADS, 0, st>>>(B.keys[cur], B.vals[cur], B.keys[cur ^ 1], B.vals[cur ^ 1], nSlots, shift, radix,
-                                                            B.radixCounts, nb, B.radixTotals, B.state);
-            }
-            shift += s->sortBits[pass];
-            cur ^= 1;
+        const uint32_t nc = static_cast<uint32_t>(s->ncells), ntiles = cdiv(nc, CS_TILE);
+        if(nSlots) {
+            LaunchScope ls(s, K_HASH_COUNT);
+            k_hash_count<<<cdiv(nSlots, 256), 256, 0, st>>>(B.posA, B.idA, B.keys[0], B.vals[0], nSlots, P, B.cellTab, B.state);
         }
-    }
-    B.keyB = B.keys[cur];
-    {
-        LaunchScope  ls(s, K_CLEAR_CELLS);
-        const size_t nvec = (s->ncells * sizeof(uint2) + 15) / 16;
-        k_clear_cells<<<std::min<uint32_t>(cdiv(nvec, 256), s->numSMs * 16), 256, 0, st>>>(reinterpret_cast<uint4*>(B.cellTab), nvec, B.state);
-    }
-    if(n) {
-        LaunchScope ls(s, K_CELL_BOUNDS);
-        k_cell_bounds_bricks<<<gridN, 256, 0, st>>>(B.keyB, n, B.cellTab, B.brickFlag, P, B.state);
+        {
+            LaunchScope ls(s, K_CELL_SCAN);
+            k_cell_scan_reduce<<<ntiles, CS_THREADS, 0, st>>>(B.cellTab, nc, s->cellTileSums, B.state);
+            k_radix_scan<<<1, 1024, 0, st>>>(s->cellTileSums, ntiles, B.radixTotals, B.state);
+            k_cell_scan_apply<<<ntiles, CS_THREADS, 0, st>>>(B.cellTab, nc, s->cellTileSums, B.brickFlag, P, B.state);
+        }
+        if(nSlots) {
+            LaunchScope ls(s, K_COUNT_SCATTER);
+            k_count_scatter<<<cdiv(nSlots, 256), 256, 0, st>>>(B.keys[0], B.vals[0], B.cellTab, B.keys[1], B.vals[1], nSlots, B.state);
+        }
+        cur    = 1;
+        B.keyB = B.keys[1];
+    } else {
+        if(nSlots) {
+            {
+                LaunchScope ls(s, K_HASH);
+                k_hash<<<cdiv(nSlots, 256), 256, 0, st>>>(B.posA, B.idA, B.keys[0], B.vals[0], nSlots, P, B.state);
+            }
+            const uint32_t nb    = cdiv(nSlots, RS_TILE);
+            int            shift = 0;
+            for(int pass = 0; pass < s->sortPasses; ++pass) {
+                const int radix = 1 << s->sortBits[pass];
+                {
+                    LaunchScope ls(s, K_RADIX_HIST);
+                    k_radix_hist<<<nb, RS_THREADS, 0, st>>>(B.keys[cur], nSlots, shift, radix, B.radixCounts, nb, B.state);
+                }
+                {
+                    LaunchScope ls(s, K_RADIX_SCAN);
+                    k_radix_scan<<<radix, 1024, 0, st>>>(B.radixCounts, nb, B.radixTotals, B.state);
+                }
+                {
+                    LaunchScope ls(s, K_RADIX_SCATTER);
+                    k_radix_scatter<<<nb, RS_THREADS, 0, st>>>(B.keys[cur], B.vals[cur], B.keys[cur ^ 1], B.vals[cur ^ 1], nSlots, shift, radix,
+                                                                B.radixCounts, nb, B.radixTotals, B.state);
+                }
+                shift += s->sortBits[pass];
+                cur ^= 1;
+            }
+        }
+        B.keyB = B.keys[cur];
+        {
+            LaunchScope  ls(s, K_CLEAR_CELLS);
+            const size_t nvec = (s->ncells * sizeof(uint2) + 15) / 16;
+            k_clear_cells<<<std::min<uint32_t>(cdiv(nvec, 256), s->numSMs * 16), 256, 0, st>>>(reinterpret_cast<uint4*>(B.cellTab), nvec, B.state);
+        }
+        if(n) {
+            LaunchScope ls(s, K_CELL_BOUNDS);
+            k_cell_bounds_bricks<<<gridN, 256, 0, st>>>(B.keyB, n, B.cellTab, B.brickFlag, P, B.state);
+        }
     }
     {
         LaunchScope ls(s, K_BRICK_COMPACT);
@@ -365,16 +400,25 @@ int enqueue_substep_launches(sf_solver* s)
     if(n) {
         {
             LaunchScope ls(s, K_REORDER);
-            k_reorder<<<gridN, 256, 0, st>>>(B.keyB, B.vals[cur], B.cellTab, B.posA, B.velA, B.idA, B.posB, B.velB, B.idB, n, B.state);
+            if(velHostXYZ) k_reorder_pos<<<gridN, 256, 0, st>>>(B.keyB, B.vals[cur], B.cellTab, B.posA, B.idA, B.posB, B.idB, n, B.state);
+            else k_reorder<<<gridN, 256, 0, st>>>(B.keyB, B.vals[cur], B.cellTab, B.posA, B.velA, B.idA, B.posB, B.velB, B.idB, n, B.state);
         }
         {
             LaunchScope ls(s, K_DENSITY);
-            k_density_brick<<<std::min<uint32_t>(pairGrid, s->numSMs * s->occDensity), kBrickThreads, kSmemDensity, st>>>(B, P);
+            if(s->densityH == 1) k_density_brick_h<1><<<std::min<uint32_t>(pairGrid, s->numSMs * s->occDensity), kBrickThreads, kSmemDensityH, st>>>(B, P);
+            else if(s->densityH == 2) k_density_brick_h<2><<<std::min<uint32_t>(pairGrid, s->numSMs * s->occDensity), kBrickThreads, kSmemDensityH, st>>>(B, P);
+            else k_density_brick<<<std::min<uint32_t>(pairGrid, s->numSMs * s->occDensity), kBrickThreads, kSmemDensity, st>>>(B, P);
         }
         if(P.correctDensity) {
             LaunchScope ls(s, K_CORRECT_DENSITY);
             k_correct_density<<<gridN, 256, 0, st>>>(B, P);
             k_density_terms<<<gridN, 256, 0, st>>>(B, P);
+        }
+        if(velHostXYZ) {
+            SF_CUDA(s, cudaStreamWaitEvent(st, s->evVelUp, 0));
+            LaunchScope ls(s, K_MARSHAL);
+            k_gather_vel_host<<<gridN, 256, 0, st>>>(velHostXYZ, B.idB, B.velB, n, B.state);
+            k_begin_step<<<1, 1, 0, st>>>(B.state, P, kBeginClock);
         }
         {
             LaunchScope ls(s, K_FORCE);
@@ -654,6 +698,8 @@ int sf_create(const sf_params* p, int device, sf_solver** out)
     if(e == cudaSuccess) e = cudaEventCreate(&s->timerA);
     if(e == cudaSuccess) e = cudaEventCreate(&s->timerB);
     if(e == cudaSuccess) e = cudaFuncSetAttribute(k_density_brick, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemDensity));
+    if(e == cudaSuccess) e = cudaFuncSetAttribute(k_density_brick_h<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemDensityH));
+    if(e == cudaSuccess) e = cudaFuncSetAttribute(k_density_brick_h<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemDensityH));
     if(e == cudaSuccess) e = cudaFuncSetAttribute(k_force_brick, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemPair));
     if(e == cudaSuccess) e = cudaFuncSetAttribute(k_visc_brick, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemPair));
     if(e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->occDensity, k_density_brick, kBrickThreads, kSmemDensity);
@@ -666,6 +712,8 @@ int sf_create(const sf_params* p, int device, sf_solver** out)
     }
     s->stream = s->ownStream;
     s->useGraph = std::getenv("SF_NO_GRAPH") == nullptr;
+    if(const char* m = std::getenv("SF_SORT")) s->countSort = std::strcmp(m, "count") == 0;
+    if(const char* m = std::getenv("SF_DENSITY")) s->densityH = std::strcmp(m, "h") == 0 ? 1 : (std::strcmp(m, "h2") == 0 ? 2 : 0);
     s->occDensity = std::max(s->occDensity, 1);
     s->occForce   = std::max(s->occForce, 1);
     s->occVisc    = std::max(s->occVisc, 1);
@@ -687,6 +735,15 @@ void sf_destroy(sf_solver* s)
     cudaFree(B.cellTab); cudaFree(B.rho); cudaFree(B.rho2); cudaFree(B.accel); cudaFree(B.nbrL); cudaFree(B.nbrCnt); cudaFree(B.brickFlag); cudaFree(B.brickList);
     cudaFree(B.tabW); cudaFree(B.tabG); cudaFree(B.bnd); cudaFree(B.radixCounts); cudaFree(B.radixTotals); cudaFree(B.state);
     cudaFree(s->stage);
+    cudaFree(s->cellTileSums);
+    if(s->xferStream) {
+        cudaStreamSynchronize(s->xferStream);
+        cudaStreamDestroy(s->xferStream);
+        cudaEventDestroy(s->evPosUp);
+        cudaEventDestroy(s->evVelUp);
+        cudaEventDestroy(s->evPosOut);
+        cudaEventDestroy(s->evVelOut);
+    }
     if(s->snapStream) {
         cudaStreamSynchronize(s->snapStream);
         cudaStreamDestroy(s->snapStream);
@@ -851,6 +908,10 @@ int sf_make_ready(sf_solver* s)
         SF_CUDA(s, dev_alloc(s->B.cellTab, s->ncells + 2));
         s->cellCap = s->ncells;
     }
+    if(s->countSort && (s->ncells > s->cellTileCap || !s->cellTileSums)) {
+        SF_CUDA(s, dev_alloc(s->cellTileSums, static_cast<size_t>(cdiv(s->ncells, CS_TILE)) + 1));
+        s->cellTileCap = s->ncells;
+    }
     {
         const uint32_t nb = static_cast<uint32_t>((s->grid[0] + BX - 1) / BX) * ((s->nM() + BY - 1) / BY) * ((s->nS() + zPad + BZ - 1) / BZ);
         if(nb > s->brickCap || !s->B.brickFlag) {
@@ -1008,47 +1069,91 @@ int sf_step_host(sf_solver* s, float* pos_xyz, float* vel_xyz, uint32_t n, float
 {
     if(!s || !pos_xyz || !vel_xyz) return SF_ERR_INVALID;
     if(s->slab.on) return fail(s, SF_ERR_INVALID, "slab mode: use sf_upload_local / sf_advance_frame / sf_download_local");
-    const bool sameShape = s->uploaded && s->ready && n == s->n;
+    const bool sameShape = s->uploaded && s->ready && n == s->n && n > 0;
     int        rc;
     if(!sameShape) {
         rc = sf_upload_particles(s, pos_xyz, vel_xyz, n);
         if(rc) return rc;
         rc = sf_make_ready(s);
         if(rc) return rc;
+        rc = enqueue_substep(s);
+        if(rc) return rc;
+        if(n) {
+            LaunchScope ls(s, K_MARSHAL);
+            float*      dpos = s->stage;
+            float*      dvel = s->stage + 3 * static_cast<size_t>(s->npad);
+            k_unpack_xyz<<<cdiv(n, 256), 256, 0, s->stream>>>(s->B.posA, s->B.idA, dpos, n);
+            k_unpack_xyz<<<cdiv(n, 256), 256, 0, s->stream>>>(s->B.velA, s->B.idA, dvel, n);
+            SF_CUDA(s, cudaMemcpyAsync(pos_xyz, dpos, static_cast<size_t>(n) * 12, cudaMemcpyDeviceToHost, s->stream));
+            SF_CUDA(s, cudaMemcpyAsync(vel_xyz, dvel, static_cast<size_t>(n) * 12, cudaMemcpyDeviceToHost, s->stream));
+        }
     } else {
-        // steady state: same particle count, overwrite the device state from the host buffers.
-        // The state is re-packed in upload order (id = index), so the previous sort order is dropped.
+        // Steady state: same particle count; the device state is overwritten from the host buffers (upload order,
+        // id = index, so the previous sort order is dropped).  The copies run on a second stream:
+        //   copy stream   : H2D positions | H2D velocities ........................ | D2H positions | D2H velocities
+        //   compute stream:               | sort, cell tables, density | v gather, dt, force, XSPH + integrate | unpack
+        // Sorting and the density pass need positions only, so the velocity upload hides behind them.
         SF_CUDA(s, cudaSetDevice(s->device));
-        float* dpos = s->stage;
-        float* dvel = s->stage + 3 * static_cast<size_t>(s->npad);
-        SF_CUDA(s, cudaMemcpyAsync(dpos, pos_xyz, static_cast<size_t>(n) * 12, cudaMemcpyHostToDevice, s->stream));
-        SF_CUDA(s, cudaMemcpyAsync(dvel, vel_xyz, static_cast<size_t>(n) * 12, cudaMemcpyHostToDevice, s->stream));
-        {
-            LaunchScope ls(s, K_MARSHAL);
-            k_pack_upload<<<cdiv(n, 256), 256, 0, s->stream>>>(dpos, dvel, s->B.posA, s->B.velA, s->B.idA, n);
+        if(!s->xferStream) {
+            SF_CUDA(s, cudaStreamCreateWithFlags(&s->xferStream, cudaStreamNonBlocking));
+            SF_CUDA(s, cudaEventCreateWithFlags(&s->evPosUp, cudaEventDisableTiming));
+            SF_CUDA(s, cudaEventCreateWithFlags(&s->evVelUp, cudaEventDisableTiming));
+            SF_CUDA(s, cudaEventCreateWithFlags(&s->evPosOut, cudaEventDisableTiming));
+            SF_CUDA(s, cudaEventCreateWithFlags(&s->evVelOut, cudaEventDisableTiming));
         }
+        cudaStream_t cs = s->stream, xs = s->xferStream;
+        float*       dpos = s->stage;
+        float*       dvel = s->stage + 3 * static_cast<size_t>(s->npad);
+        const size_t bytes = static_cast<size_t>(n) * 12;
+        SF_CUDA(s, cudaMemcpyAsync(dpos, pos_xyz, bytes, cudaMemcpyHostToDevice, xs));
+        SF_CUDA(s, cudaEventRecord(s->evPosUp, xs));
+        SF_CUDA(s, cudaMemcpyAsync(dvel, vel_xyz, bytes, cudaMemcpyHostToDevice, xs));
+        SF_CUDA(s, cudaEventRecord(s->evVelUp, xs));
         DevState init{};
-        init.maxv2Bits[0] = init.maxv2Bits[1] = 0x00800000u;
-        SF_CUDA(s, cudaMemcpyAsync(s->B.state, &init, sizeof(init), cudaMemcpyHostToDevice, s->stream));
+        init.maxv2Bits[0] = init.maxv2Bits[1] = 0x00800000u; // FLT_MIN
+        *s->hostState = init; // pinned: the asynchronous copy below reads it when the stream gets there
+        SF_CUDA(s, cudaMemcpyAsync(s->B.state, s->hostState, sizeof(DevState), cudaMemcpyHostToDevice, cs));
+        SF_CUDA(s, cudaStreamWaitEvent(cs, s->evPosUp, 0));
         {
             LaunchScope ls(s, K_MARSHAL);
-            k_init_maxvel<<<std::min<uint32_t>(cdiv(n, 256), s->numSMs * 8), 256, 0, s->stream>>>(s->B.velA, n, s->B.state);
+            k_pack_pos<<<cdiv(n, 256), 256, 0, cs>>>(dpos, s->B.posA, s->B.idA, n);
         }
-    }
-    rc = enqueue_substep(s);
-    if(rc) return rc;
-    {
-        LaunchScope ls(s, K_MARSHAL);
-        float*      dpos = s->stage;
-        float*      dvel = s->stage + 3 * static_cast<size_t>(s->npad);
-        k_unpack_xyz<<<cdiv(n, 256), 256, 0, s->stream>>>(s->B.posA, s->B.idA, dpos, n);
-        k_unpack_xyz<<<cdiv(n, 256), 256, 0, s->stream>>>(s->B.velA, s->B.idA, dvel, n);
-        SF_CUDA(s, cudaMemcpyAsync(pos_xyz, dpos, static_cast<size_t>(n) * 12, cudaMemcpyDeviceToHost, s->stream));
-        SF_CUDA(s, cudaMemcpyAsync(vel_xyz, dvel, static_cast<size_t>(n) * 12, cudaMemcpyDeviceToHost, s->stream));
+        rc = enqueue_substep_launches(s, dvel);
+        if(rc) return rc;
+        {
+            LaunchScope ls(s, K_MARSHAL);
+            k_unpack_xyz<<<cdiv(n, 256), 256, 0, cs>>>(s->B.posA, s->B.idA, dpos, n);
+            SF_CUDA(s, cudaEventRecord(s->evPosOut, cs));
+            k_unpack_xyz<<<cdiv(n, 256), 256, 0, cs>>>(s->B.velA, s->B.idA, dvel, n);
+            SF_CUDA(s, cudaEventRecord(s->evVelOut, cs));
+        }
+        SF_CUDA(s, cudaStreamWaitEvent(xs, s->evPosOut, 0));
+        SF_CUDA(s, cudaMemcpyAsync(pos_xyz, dpos, bytes, cudaMemcpyDeviceToHost, xs));
+        SF_CUDA(s, cudaStreamWaitEvent(xs, s->evVelOut, 0));
+        SF_CUDA(s, cudaMemcpyAsync(vel_xyz, dvel, bytes, cudaMemcpyDeviceToHost, xs));
     }
     rc = read_state(s);
     if(rc) return rc;
+    if(s->xferStream) SF_CUDA(s, cudaStreamSynchronize(s->xferStream));
     if(dt_out) *dt_out = s->hostState->dt;
+    return SF_OK;
+}
+
+int sf_host_alloc(uint64_t bytes, void** out)
+{
+    if(!out) return SF_ERR_INVALID;
+    *out = nullptr;
+    if(bytes == 0) return SF_OK;
+    const cudaError_t e = cudaMallocHost(out, bytes);
+    if(e != cudaSuccess) return fail(nullptr, e == cudaErrorMemoryAllocation ? SF_ERR_OOM : SF_ERR_CUDA, std::string("cudaMallocHost: ") + cudaGetErrorString(e));
+    return SF_OK;
+}
+
+int sf_host_free(void* p)
+{
+    if(!p) return SF_OK;
+    const cudaError_t e = cudaFreeHost(p);
+    if(e != cudaSuccess) return fail(nullptr, SF_ERR_CUDA, std::string("cudaFreeHost: ") + cudaGetErrorString(e));
     return SF_OK;
 }
 

@@ -13,6 +13,8 @@
 namespace sf
 {
 constexpr int kTab = 10000;
+// work unit of the pair kernels (sf_pairs.cuh): a brick of BX x BY x BZ grid cells
+constexpr int BX = 8, BY = 4, BZ = 4;
 
 // ------------------------------------------------------------------------------------------------
 // small helpers
@@ -66,15 +68,22 @@ __device__ __forceinline__ int wall_of(const DevParams& P, const float4& x)
 // ------------------------------------------------------------------------------------------------
 // Substep prologue: computeTimeStep (A.5) from the max |v|^2 the previous substep's integrate
 // kernel reduced, and the frame-time bookkeeping of Simulator::doSimulation (Simulator.cpp:46-51).
-__global__ void k_begin_step(DevState* st, DevParams P)
+// phases: bit 0 = work-queue resets (needed before the cell tables are built), bit 1 = dt and the frame clock
+// (needed before the force pass).  The resident path launches both at once; sf_step_host launches them apart so
+// that the velocity upload (which max |v|^2 and hence dt depend on) overlaps the sort and the density pass.
+constexpr int kBeginResets = 1, kBeginClock = 2, kBeginAll = 3;
+__global__ void k_begin_step(DevState* st, DevParams P, int phases)
 {
-    if(st->frameTarget > 0.0 && !(static_cast<double>(st->frameTime) < st->frameTarget)) {
-        st->skip = 1;
-        return;
+    if(phases & kBeginResets) {
+        if(st->frameTarget > 0.0 && !(static_cast<double>(st->frameTime) < st->frameTarget)) {
+            st->skip = 1;
+            return;
+        }
+        st->skip          = 0;
+        st->brickCount    = 0u;
+        st->cursor[0] = st->cursor[1] = st->cursor[2] = st->cursor[3] = 0u;
     }
-    st->skip          = 0;
-    st->brickCount    = 0u;
-    st->cursor[0] = st->cursor[1] = st->cursor[2] = st->cursor[3] = 0u;
+    if(!(phases & kBeginClock) || st->skip) return;
     const unsigned pr = st->step & 1u;
     const float    M  = __uint_as_float(st->maxv2Bits[pr]);
     const float    maxv = sqrtf(M);
@@ -276,6 +285,112 @@ k_radix_scatter(const uint32_t* __restrict__ keysIn, const uint32_t* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
+// (1') counting sort by cell key -- the alternative to the radix passes (SF_SORT=count).  A cell key has up to 27
+//      bits but only ~8 particles share one, and k_reorder re-ranks every cell by original id anyway, so the order
+//      in which particles arrive inside a cell is irrelevant:
+//        k_clear_cells -> k_hash_count (key + arrival rank in its cell, warp-aggregated atomics on cellTab[key].y)
+//        -> k_cell_scan_reduce / k_radix_scan (tile sums) / k_cell_scan_apply (cellTab = {begin,end}, brick flags)
+//        -> k_count_scatter (slot permutation in key order)
+//      One pass over the particles and one over the cells instead of three passes of (histogram, scan, scatter).
+constexpr int CS_THREADS = 256;
+constexpr int CS_ITEMS   = 8;
+constexpr int CS_TILE    = CS_THREADS * CS_ITEMS;
+
+__global__ void k_hash_count(const float4* __restrict__ pos, const uint32_t* __restrict__ id, uint32_t* __restrict__ keys,
+                             uint32_t* __restrict__ ranks, uint32_t nSlots, DevParams P, uint2* __restrict__ cellTab, const DevState* st)
+{
+    if(st->skip) return;
+    const uint32_t i    = blockIdx.x * blockDim.x + threadIdx.x; // blockDim.x is a multiple of 32: whole warps reach the match
+    const int      lane = threadIdx.x & 31;
+    const bool     live = i < nSlots && id[i] != kInvalidId;
+    const uint32_t key  = live ? cell_key(P, pos[i]) : 0xffffffffu;
+    const uint32_t peers  = __match_any_sync(0xffffffffu, key);
+    const int      leader = __ffs(peers) - 1;
+    uint32_t       base   = 0u;
+    if(live && lane == leader) base = atomicAdd(&cellTab[key].y, static_cast<uint32_t>(__popc(peers)));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if(i < nSlots) {
+        keys[i]  = key;
+        ranks[i] = base + __popc(peers & ((1u << lane) - 1u));
+    }
+}
+
+__global__ void __launch_bounds__(CS_THREADS)
+k_cell_scan_reduce(const uint2* __restrict__ cellTab, uint32_t ncells, uint32_t* __restrict__ tileSums, const DevState* st)
+{
+    if(st->skip) return;
+    __shared__ uint32_t warpSum[CS_THREADS / 32];
+    const uint32_t base = blockIdx.x * CS_TILE + threadIdx.x * CS_ITEMS;
+    uint32_t       sum  = 0u;
+#pragma unroll
+    for(int r = 0; r < CS_ITEMS; ++r)
+        if(base + r < ncells) sum += cellTab[base + r].y;
+    for(int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if((threadIdx.x & 31) == 0) warpSum[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if(threadIdx.x == 0) {
+        uint32_t t = 0u;
+        for(int w = 0; w < CS_THREADS / 32; ++w) t += warpSum[w];
+        tileSums[blockIdx.x] = t;
+    }
+}
+
+// tileSums have been exclusive-scanned in place (k_radix_scan with one row)
+__global__ void __launch_bounds__(CS_THREADS)
+k_cell_scan_apply(uint2* __restrict__ cellTab, uint32_t ncells, const uint32_t* __restrict__ tileSums, uint32_t* __restrict__ brickFlag,
+                  DevParams P, const DevState* st)
+{
+    if(st->skip) return;
+    __shared__ uint32_t warpSum[CS_THREADS / 32];
+    const int      lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t base = blockIdx.x * CS_TILE + threadIdx.x * CS_ITEMS;
+    uint32_t       cnt[CS_ITEMS];
+    uint32_t       sum = 0u;
+#pragma unroll
+    for(int r = 0; r < CS_ITEMS; ++r) {
+        cnt[r] = base + r < ncells ? cellTab[base + r].y : 0u;
+        sum += cnt[r];
+    }
+    uint32_t x = sum; // inclusive scan of the per-thread sums over the warp, then over the warps
+    for(int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if(lane >= o) x += y;
+    }
+    if(lane == 31) warpSum[wid] = x;
+    __syncthreads();
+    uint32_t off = tileSums[blockIdx.x] + x - sum;
+    for(int w = 0; w < wid; ++w) off += warpSum[w];
+#pragma unroll
+    for(int r = 0; r < CS_ITEMS; ++r) {
+        if(base + r < ncells) {
+            const uint32_t c = cnt[r];
+            cellTab[base + r] = c ? make_uint2(off, off + c) : make_uint2(0u, 0u);
+            if(c) {
+                const uint32_t key = base + r;
+                const int      cx = static_cast<int>(key % static_cast<uint32_t>(P.nx));
+                const int      t  = static_cast<int>(key / static_cast<uint32_t>(P.nx));
+                const int      cy = t % P.ny, cz = t / P.ny;
+                brickFlag[((cz / BZ) * P.nby + (cy / BY)) * P.nbx + (cx / BX)] = 1u; // == brick_of_key (sf_pairs.cuh)
+            }
+            off += c;
+        }
+    }
+}
+
+__global__ void k_count_scatter(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ ranks, const uint2* __restrict__ cellTab,
+                                uint32_t* __restrict__ keysOut, uint32_t* __restrict__ slotsOut, uint32_t nSlots, const DevState* st)
+{
+    if(st->skip) return;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= nSlots) return;
+    const uint32_t key = keys[i];
+    if(key == 0xffffffffu) return; // dead slot (last substep's ghost)
+    const uint32_t dst = cellTab[key].x + ranks[i];
+    keysOut[dst]  = key;
+    slotsOut[dst] = i;
+}
+
+// ------------------------------------------------------------------------------------------------
 // (1) cell start/end tables + particle reorder
 __global__ void k_clear_cells(uint4* __restrict__ tab, size_t nvec, const DevState* st)
 {
@@ -309,6 +424,53 @@ __global__ void k_reorder(const uint32_t* __restrict__ keys, const uint32_t* __r
     posB[dst]          = x;
     velB[dst]          = v;
     idB[dst]           = myId;
+}
+
+// sf_step_host variants (velocity upload overlapped with sort + density): k_reorder without the velocity gather ...
+__global__ void k_reorder_pos(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                              const uint2* __restrict__ cellTab, const float4* __restrict__ posA,
+                              const uint32_t* __restrict__ idA, float4* __restrict__ posB, uint32_t* __restrict__ idB,
+                              uint32_t n, const DevState* st)
+{
+    if(st->skip) return;
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if(p >= n) return;
+    const uint32_t src  = vals[p];
+    const uint32_t myId = idA[src];
+    const uint2    ce   = cellTab[keys[p]];
+    uint32_t       rank = 0;
+    for(uint32_t q = ce.x; q < ce.y; ++q) rank += (idA[vals[q]] < myId) ? 1u : 0u;
+    const uint32_t dst = ce.x + rank;
+    float4         x   = posA[src];
+    x.w                = 0.f;
+    posB[dst]          = x;
+    idB[dst]           = myId;
+}
+
+// ... and the velocity gather straight from the uploaded xyz array (id = upload index) once it has arrived, keeping
+// velB.w = 1/rho of the density pass, fused with computeMaxVel (A.5) of the uploaded velocities
+__global__ void k_gather_vel_host(const float* __restrict__ velXYZ, const uint32_t* __restrict__ idB, float4* __restrict__ velB,
+                                  uint32_t n, DevState* st)
+{
+    if(st->skip) return;
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    float          m = FLT_MIN;
+    if(p < n) {
+        const size_t o = 3 * static_cast<size_t>(idB[p]);
+        const float  vx = velXYZ[o], vy = velXYZ[o + 1], vz = velXYZ[o + 2];
+        velB[p]        = make_float4(vx, vy, vz, velB[p].w);
+        m              = fmaxf(m, (vy * vy + vx * vx) + vz * vz);
+    }
+    for(int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if((threadIdx.x & 31) == 0 && m > FLT_MIN) atomicMax(&st->maxv2Bits[st->step & 1u], __float_as_uint(m));
+}
+
+__global__ void k_pack_pos(const float* __restrict__ posXYZ, float4* __restrict__ pos, uint32_t* __restrict__ id, uint32_t n)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    pos[i] = make_float4(posXYZ[3 * i], posXYZ[3 * i + 1], posXYZ[3 * i + 2], 0.f);
+    id[i]  = i;
 }
 
 // ------------------------------------------------------------------------------------------------
