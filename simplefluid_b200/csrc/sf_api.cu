@@ -65,8 +65,9 @@ struct sf_solver {
     size_t       stageBytes = 0;
     DevState*    hostState = nullptr; // pinned
     uint32_t     radixBlocks = 0;
-    int          densityH  = 0;          // SF_DENSITY=h / h2: half-precision candidate filter (k_density_brick_h<1> / <2>)
-    bool         countSort = false;      // SF_SORT=count: counting sort by cell instead of the radix passes
+    // Kernel variants, all bit-identical (tools/variant_bench.py); the environment overrides exist for A/B timing:
+    int          densityH  = 1;          // SF_DENSITY=h (default) / h2: half-precision candidate filter k_density_brick_h<1> / <2>; q: fp32 filter queue
+    bool         countSort = true;       // SF_SORT=count (default): counting sort by cell; radix: three LSD radix passes
     uint32_t*    cellTileSums = nullptr; // counting sort: per-tile particle counts of the cell table
     uint64_t     cellTileCap = 0;
     int          sortPasses = 0, sortBits[4] = { 0, 0, 0, 0 };
@@ -712,8 +713,8 @@ int sf_create(const sf_params* p, int device, sf_solver** out)
     }
     s->stream = s->ownStream;
     s->useGraph = std::getenv("SF_NO_GRAPH") == nullptr;
-    if(const char* m = std::getenv("SF_SORT")) s->countSort = std::strcmp(m, "count") == 0;
-    if(const char* m = std::getenv("SF_DENSITY")) s->densityH = std::strcmp(m, "h") == 0 ? 1 : (std::strcmp(m, "h2") == 0 ? 2 : 0);
+    if(const char* m = std::getenv("SF_SORT")) s->countSort = std::strcmp(m, "radix") != 0;
+    if(const char* m = std::getenv("SF_DENSITY")) s->densityH = std::strcmp(m, "q") == 0 ? 0 : (std::strcmp(m, "h2") == 0 ? 2 : 1);
     s->occDensity = std::max(s->occDensity, 1);
     s->occForce   = std::max(s->occForce, 1);
     s->occVisc    = std::max(s->occVisc, 1);
