@@ -67,6 +67,7 @@ struct sf_solver {
     uint32_t     radixBlocks = 0;
     // Kernel variants, all bit-identical (tools/variant_bench.py); the environment overrides exist for A/B timing:
     int          densityH  = 1;          // SF_DENSITY=h (default) / h2: half-precision candidate filter k_density_brick_h<1> / <2>; q: fp32 filter queue
+    bool         listTiled = true;       // SF_LIST=tiled (default): [slot/32][k][slot%32]; ell: [k][slot]
     bool         countSort = true;       // SF_SORT=count (default): counting sort by cell; radix: three LSD radix passes
     uint32_t*    cellTileSums = nullptr; // counting sort: per-tile particle counts of the cell table
     uint64_t     cellTileCap = 0;
@@ -236,6 +237,7 @@ void fill_dev_params(sf_solver* s)
     P.n    = s->n;
     P.npad = s->npad;
     P.kmax = s->kmax;
+    P.listTiled = s->listTiled ? 1 : 0;
     P.nbx  = (s->grid[0] + BX - 1) / BX;
     P.nby  = (s->nM() + BY - 1) / BY;
     P.nbz  = (s->nS() + BZ - 1) / BZ;
@@ -713,6 +715,7 @@ int sf_create(const sf_params* p, int device, sf_solver** out)
     }
     s->stream = s->ownStream;
     s->useGraph = std::getenv("SF_NO_GRAPH") == nullptr;
+    if(const char* m = std::getenv("SF_LIST")) s->listTiled = std::strcmp(m, "ell") != 0;
     if(const char* m = std::getenv("SF_SORT")) s->countSort = std::strcmp(m, "radix") != 0;
     if(const char* m = std::getenv("SF_DENSITY")) s->densityH = std::strcmp(m, "q") == 0 ? 0 : (std::strcmp(m, "h2") == 0 ? 2 : 1);
     s->occDensity = std::max(s->occDensity, 1);

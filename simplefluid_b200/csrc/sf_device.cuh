@@ -13,8 +13,8 @@
 //   brickList     : ids of the non-empty cell bricks (BX x BY x BZ cells) of this substep, in z-major
 //                   order; the three pair kernels are persistent CTAs that pull bricks from it
 //   nbrL          : neighbour list built once per substep by the density pass and reused by the
-//                   force and viscosity passes: ELL layout [k][slot] (row stride npad) so a warp
-//                   reads/writes 128 B rows; entry = brick-local halo index of the neighbour (16 bit,
+//                   force and viscosity passes: [slot/32][k][slot%32], so a warp reads/writes 128 B
+//                   rows and the rows of 32 slots are one contiguous block; entry = brick-local halo index of the neighbour (16 bit,
 //                   or wall-particle index) | kernel-table index min(trunc(sqrt(d2)*invStep), 10000)
 //                   << 16, the index being shared by the cubic-W and spiky-grad tables
 //   nbrCnt        : packed counts: fluid (14 bit) | wallX (6) | wallY (6) | wallZ (6);
@@ -50,6 +50,7 @@ struct DevParams {
     // cell counts and every "z"/"layer" of the slab logic means the slow axis.  The 3x3 rows of a neighbourhood
     // are always visited in the reference's order (dz outer, dy inner).
     int      axisS;
+    int      listTiled;   // neighbour-list layout: 1 = [slot/32][k][slot%32] (default), 0 = ELL [k][slot]
     uint32_t nbnd[6];     // wall particle counts
     uint32_t bndStride;   // slots per wall in the bnd array
 };

@@ -1,7 +1,7 @@
-"""Compare the selectable kernel variants (SF_SORT=radix|count, SF_DENSITY=q|h|h2) on one GPU:
+"""Compare the selectable kernel variants (SF_SORT=radix|count, SF_DENSITY=q|h|h2, SF_LIST=tiled|ell) on one GPU:
 bit-equality of the state after `steps` substeps against the first variant, per-kernel times, and the
 host-buffer step.  Development aid; usage:  python tools/variant_bench.py [res] [steps] [variant ...]
-where a variant is e.g. radix+q, count+h."""
+where a variant is e.g. radix+q, count+h, count+h+ell (third field: neighbour-list layout, tiled by default)."""
 import os
 import sys
 import time
@@ -14,9 +14,10 @@ import simplefluid_b200 as sf  # noqa: E402
 
 
 def make(scene, res, variant):
-    sort, dens = variant.split("+")
-    os.environ["SF_SORT"] = sort
-    os.environ["SF_DENSITY"] = dens
+    parts = variant.split("+")
+    os.environ["SF_SORT"] = parts[0]
+    os.environ["SF_DENSITY"] = parts[1]
+    os.environ["SF_LIST"] = parts[2] if len(parts) > 2 else "tiled"
     p = sf.default_params(res, scene)
     pos = sf.scene_generate(p)
     gpu = sf.SPHSolver(p)  # the variant is read at sf_create
