@@ -257,6 +257,47 @@ def test_crowded_cells_collisions(sf, ob):
     orc.close()
 
 
+@pytest.mark.parametrize("env", [dict(SF_SORT="radix"), dict(SF_DENSITY="q"), dict(SF_LIST="ell"),
+                                 dict(SF_SORT="radix", SF_DENSITY="q", SF_LIST="ell")])
+def test_kernel_variants_bit_identical(sf, ob, monkeypatch, env):
+    """The selectable kernel variants (radix passes instead of the counting sort, fp32 filter queue instead of the
+    half-precision filter, ELL instead of the tiled neighbour list; read at sf_create) give the oracle's bits too."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    gpu, orc, _ = make_pair(sf, ob, "DoubleDambreak", 40)
+    ocnt, oids = orc.neighbors()
+    assert orc.advance() == gpu.advanceFrame()
+    check_step_fields(gpu, orc, ocnt, oids)
+    for _ in range(30):
+        assert orc.advance() == gpu.advanceFrame()
+    assert exact(gpu.getParticles(), orc.positions()) and exact(gpu.getVelocity(), orc.velocities())
+    assert exact(gpu.density(), orc.density())
+    gpu.close()
+    orc.close()
+
+
+def test_pinned_host_buffers_step(sf, ob):
+    """sf_host_alloc buffers through sf_step_host: the overlapped copy path (positions first, velocities behind
+    sort + density) on page-locked memory equals the oracle."""
+    p = sf.default_params(32, "Dambreak")
+    pos = sf.scene_generate(p)
+    gpu = sf.SPHSolver(p)
+    gpu.generateBoundaryParticles(0)
+    hx, hv = sf.PinnedArray(pos.shape), sf.PinnedArray(pos.shape)
+    hx.array[:] = pos
+    hv.array[:] = 0.0
+    hv.array[::7, 0] = 0.25  # moving particles: dt must follow the uploaded velocities
+    orc = ob.Oracle(ob.default_params(32, "Dambreak"), pos, hv.array.copy(), boundary_seed=0)
+    for _ in range(6):
+        dto = orc.advance()
+        assert gpu.stepHost(hx.array, hv.array) == dto
+        assert exact(hx.array, orc.positions()) and exact(hv.array, orc.velocities())
+    gpu.close()
+    orc.close()
+    hx.close()
+    hv.close()
+
+
 def test_full_size_properties_double_dambreak_8m(sf):
     """configs[2] at full size (8,028,160 particles): properties that need no oracle -- determinism
     (two runs bit-identical), the sort is a permutation, neighbour relation symmetric, particles stay in
