@@ -156,8 +156,10 @@ int sf_download_field(sf_solver* s, int field, void* out, uint64_t bytes);
 int sf_grid_dims(sf_solver* s, int32_t n3[3]);                     /* Grid3D::setGrid EXE@0x14001ab20 */
 
 /* ---- measurement ---------------------------------------------------------------------------- */
-/* Per-kernel CUDA-event timing on the launching stream.  names: NUL-separated list written into
- * buf; ms/launches arrays of length cap.  Returns the number of kernels via *count_out. */
+/* Per-kernel CUDA-event timing on the launching stream.  sf_profile_enable(s, N): every N-th substep is timed
+ * kernel by kernel (direct launches bracketed by events; the others keep the CUDA-graph replay), N = 1: every
+ * substep, 0: off.  names: NUL-separated list written into buf; ms/launches arrays of length cap.  Returns the
+ * number of kernels via *count_out. */
 int sf_profile_enable(sf_solver* s, int on);
 int sf_profile_reset(sf_solver* s);
 int sf_profile_get(sf_solver* s, char* names_buf, size_t names_cap, double* ms, uint64_t* launches, uint32_t cap, uint32_t* count_out);

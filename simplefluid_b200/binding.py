@@ -436,8 +436,9 @@ class SPHSolver:
         self._ck(self.L.sf_upload_local(self.h, _ptr(pos4), _ptr(vel4), _ptr(ids), n))
 
     # -- measurement
-    def profileEnable(self, on=True):
-        self._ck(self.L.sf_profile_enable(self.h, 1 if on else 0))
+    def profileEnable(self, on=True, every=1):
+        """Per-kernel event timing of every `every`-th substep (the others replay the CUDA graph)."""
+        self._ck(self.L.sf_profile_enable(self.h, int(every) if on else 0))
 
     def profileReset(self):
         self._ck(self.L.sf_profile_reset(self.h))

@@ -104,7 +104,8 @@ struct sf_solver {
     } slab;
 
     // measurement
-    bool                      profiling = false;
+    bool                      profiling = false; // the substep being enqueued is timed kernel by kernel
+    uint32_t                  profEvery = 0, profCount = 0; // sf_profile_enable(N): every N-th substep is timed (0 = off)
     double                    profMs[K_COUNT] = {};
     uint64_t                  profLaunches[K_COUNT] = {};
     std::vector<PendingEvent> pending;
@@ -441,6 +442,8 @@ int enqueue_substep_launches(sf_solver* s, const float* velHostXYZ = nullptr)
 // dominate small scenes.  Profiling and slab mode use direct launches.
 int enqueue_substep(sf_solver* s)
 {
+    // sampled per-kernel timing: the timed substeps use direct launches with events, the others the graph
+    s->profiling = s->profEvery && (s->profCount++ % s->profEvery) == 0;
     if(s->slab.on || s->profiling || !s->useGraph || s->n == 0) return enqueue_substep_launches(s);
     if(!s->stepGraph) {
         const uint64_t before = s->launches;
@@ -1299,7 +1302,9 @@ int sf_profile_enable(sf_solver* s, int on)
     if(!s) return SF_ERR_INVALID;
     cudaSetDevice(s->device);
     if(!on) fold_pending(s);
-    s->profiling = on != 0;
+    s->profEvery = on > 0 ? static_cast<uint32_t>(on) : 0u;
+    s->profCount = 0;
+    s->profiling = false;
     return SF_OK;
 }
 
