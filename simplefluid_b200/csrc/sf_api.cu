@@ -66,7 +66,6 @@ struct sf_solver {
     DevState*    hostState = nullptr; // pinned
     uint32_t     radixBlocks = 0;
     // Kernel variants, all bit-identical (tools/variant_bench.py); the environment overrides exist for A/B timing:
-    bool         densityH  = true;       // SF_DENSITY=h (default): half-precision candidate filter + hit bitmasks (k_density_brick_h); q: fp32 filter + queue
     bool         listTiled = true;       // SF_LIST=tiled (default): [slot/32][k][slot%32]; ell: [k][slot]
     bool         countSort = true;       // SF_SORT=count (default): counting sort by cell; radix: three LSD radix passes
     uint32_t*    cellTileSums = nullptr; // counting sort: per-tile particle counts of the cell table
@@ -409,8 +408,7 @@ int enqueue_substep_launches(sf_solver* s, const float* velHostXYZ = nullptr)
         }
         {
             LaunchScope ls(s, K_DENSITY);
-            if(s->densityH) k_density_brick_h<<<std::min<uint32_t>(pairGrid, s->numSMs * s->occDensity), kBrickThreads, kSmemDensityH, st>>>(B, P);
-            else k_density_brick<<<std::min<uint32_t>(pairGrid, s->numSMs * s->occDensity), kBrickThreads, kSmemDensity, st>>>(B, P);
+            k_density_brick<<<std::min<uint32_t>(pairGrid, s->numSMs * s->occDensity), kBrickThreads, kSmemDensity, st>>>(B, P);
         }
         if(P.correctDensity) {
             LaunchScope ls(s, K_CORRECT_DENSITY);
@@ -703,7 +701,6 @@ int sf_create(const sf_params* p, int device, sf_solver** out)
     if(e == cudaSuccess) e = cudaEventCreate(&s->timerA);
     if(e == cudaSuccess) e = cudaEventCreate(&s->timerB);
     if(e == cudaSuccess) e = cudaFuncSetAttribute(k_density_brick, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemDensity));
-    if(e == cudaSuccess) e = cudaFuncSetAttribute(k_density_brick_h, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemDensityH));
     if(e == cudaSuccess) e = cudaFuncSetAttribute(k_force_brick, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemPair));
     if(e == cudaSuccess) e = cudaFuncSetAttribute(k_visc_brick, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemPair));
     if(e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->occDensity, k_density_brick, kBrickThreads, kSmemDensity);
@@ -718,7 +715,6 @@ int sf_create(const sf_params* p, int device, sf_solver** out)
     s->useGraph = std::getenv("SF_NO_GRAPH") == nullptr;
     if(const char* m = std::getenv("SF_LIST")) s->listTiled = std::strcmp(m, "ell") != 0;
     if(const char* m = std::getenv("SF_SORT")) s->countSort = std::strcmp(m, "radix") != 0;
-    if(const char* m = std::getenv("SF_DENSITY")) s->densityH = std::strcmp(m, "q") != 0;
     s->occDensity = std::max(s->occDensity, 1);
     s->occForce   = std::max(s->occForce, 1);
     s->occVisc    = std::max(s->occVisc, 1);

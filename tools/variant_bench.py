@@ -1,7 +1,7 @@
-"""Compare the selectable kernel variants (SF_SORT=radix|count, SF_DENSITY=q|h|h2, SF_LIST=tiled|ell) on one GPU:
-bit-equality of the state after `steps` substeps against the first variant, per-kernel times, and the
-host-buffer step.  Development aid; usage:  python tools/variant_bench.py [res] [steps] [variant ...]
-where a variant is e.g. radix+q, count+h, count+h+ell (third field: neighbour-list layout, tiled by default)."""
+"""Compare the selectable kernel variants (SF_SORT=radix|count, SF_LIST=tiled|ell) on one GPU: bit-equality of
+the state after `steps` substeps against the first variant, per-kernel times, and the host-buffer step.
+Development aid; usage:  python tools/variant_bench.py [res] [steps] [variant ...]  where a variant is
+sort+list, e.g. count+tiled (the default), radix+tiled, count+ell."""
 import os
 import sys
 import time
@@ -16,8 +16,7 @@ import simplefluid_b200 as sf  # noqa: E402
 def make(scene, res, variant):
     parts = variant.split("+")
     os.environ["SF_SORT"] = parts[0]
-    os.environ["SF_DENSITY"] = parts[1]
-    os.environ["SF_LIST"] = parts[2] if len(parts) > 2 else "tiled"
+    os.environ["SF_LIST"] = parts[1] if len(parts) > 1 else "tiled"
     p = sf.default_params(res, scene)
     pos = sf.scene_generate(p)
     gpu = sf.SPHSolver(p)  # the variant is read at sf_create
@@ -84,6 +83,6 @@ def e2e(scene, res, steps, variant):
 if __name__ == "__main__":
     res = int(sys.argv[1]) if len(sys.argv) > 1 else 203
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
-    variants = sys.argv[3:] or ["radix+q", "count+q", "radix+h", "radix+h2", "count+h"]
+    variants = sys.argv[3:] or ["count+tiled", "radix+tiled", "count+ell"]
     run("Dambreak", res, steps, variants)
     e2e("Dambreak", res, 10, variants[0])
