@@ -104,6 +104,20 @@ def test_no_cpu_fallback(sf):
     assert "no CPU fallback" in str(e.value)
 
 
+def test_pinned_host_alloc_without_gpu(sf):
+    """sf_host_alloc (page-locked buffers for sf_step_host) reports an error instead of handing out pageable memory."""
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("GPU present")
+    with pytest.raises(sf.SFError):
+        sf.PinnedArray((16, 3))
+    assert sf.library().sf_host_free(None) == 0  # freeing nothing is fine
+
+
 def test_product_does_not_reference_oracle():
     """The oracle is test infrastructure: nothing under simplefluid_b200/ or include/ may mention it."""
     bad = []
