@@ -158,3 +158,38 @@ def test_protocol_needs_the_extra_meta_slot():
     with pytest.raises(AssertionError):
         for seed in range(200):
             broken(seed)
+
+
+def test_counting_sort_and_reorder_give_the_reference_cell_lists():
+    """Restatement of the sort pipeline (k_hash_count -> scan -> k_count_scatter -> k_reorder): whatever order the
+    atomics hand out inside a cell, re-ranking by original id yields the reference's cell lists -- cells in key order,
+    ascending particle id inside a cell (collectParticlesToCells pushes ids in ascending order, EXE@0x140016890)."""
+    import numpy as np
+    rng = np.random.default_rng(11)
+    for _ in range(20):
+        n, ncells = int(rng.integers(1, 4000)), int(rng.integers(1, 300))
+        ids = rng.permutation(n).astype(np.uint32)          # A order: last substep's sorted order, arbitrary ids
+        keys = rng.integers(0, ncells, size=n).astype(np.uint32)
+        dead = rng.random(n) < 0.1                           # slab mode: last substep's ghosts
+        count = np.zeros(ncells, np.uint32)
+        rank = np.zeros(n, np.uint32)
+        for i in rng.permutation(n):                         # arrival order of the atomics: arbitrary
+            if not dead[i]:
+                rank[i] = count[keys[i]]
+                count[keys[i]] += 1
+        begin = np.concatenate(([0], np.cumsum(count)[:-1])).astype(np.uint32)
+        live = int(count.sum())
+        slot_of = np.full(live, -1, np.int64)                # k_count_scatter
+        for i in range(n):
+            if not dead[i]:
+                slot_of[begin[keys[i]] + rank[i]] = i
+        assert (slot_of >= 0).all()
+        out = np.full(live, 0xFFFFFFFF, np.uint32)           # k_reorder: rank by id inside the cell
+        for p in range(live):
+            src = slot_of[p]
+            c = keys[src]
+            members = slot_of[begin[c]:begin[c] + count[c]]
+            out[begin[c] + np.count_nonzero(ids[members] < ids[src])] = ids[src]
+        alive = np.flatnonzero(~dead)
+        want = ids[alive][np.lexsort((ids[alive], keys[alive]))]
+        assert np.array_equal(out, want)
