@@ -3,13 +3,13 @@ sets: per warp of 32 consecutive sorted particles, the number of phase-B iterati
 the hits they have to process between two points where the warp re-converges.  Compares the current scheme (hits of
 one halo row at a time) with pooling the hits of a dz-plane (3 rows) or of all 9 rows.  Analysis aid for DESIGN.md.
 
-    python tools/phaseb_occupancy.py [scene] [res] [substeps]"""
+    python tests/tools/phaseb_occupancy.py [scene] [res] [substeps]"""
 import os
 import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import oracle_binding as ob  # noqa: E402  (test infrastructure; this tool is an analysis aid, not product code)
 
