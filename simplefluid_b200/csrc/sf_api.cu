@@ -346,6 +346,7 @@ int enqueue_substep_launches(sf_solver* s, const float* velHostXYZ = nullptr)
         }
         {
             LaunchScope ls(s, K_CELL_SCAN);
+            s->launches += 2; // three kernels under one timing scope
             k_cell_scan_reduce<<<ntiles, CS_THREADS, 0, st>>>(B.cellTab, nc, s->cellTileSums, B.state);
             k_radix_scan<<<1, 1024, 0, st>>>(s->cellTileSums, ntiles, B.radixTotals, B.state);
             k_cell_scan_apply<<<ntiles, CS_THREADS, 0, st>>>(B.cellTab, nc, s->cellTileSums, B.brickFlag, P, B.state);
