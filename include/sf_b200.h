@@ -148,12 +148,28 @@ typedef enum sf_field {
     SF_FIELD_NEIGHBOR_IDS = 5,   /* uint32[sum]   original ids, ascending per particle, concatenated in particle order */
     SF_FIELD_SORT_PERM = 6,      /* uint32[n]     original id of the particle at each sorted slot */
     SF_FIELD_TABLE_CUBIC_W = 7,  /* float[10001]  PrecomputedKernel<Cubic>  W table (A.2) */
-    SF_FIELD_TABLE_SPIKY_GRAD = 8/* float[10001]  PrecomputedKernel<Spiky> gradW/r table (A.2) */
+    SF_FIELD_TABLE_SPIKY_GRAD = 8,/* float[10001] PrecomputedKernel<Spiky> gradW/r table (A.2) */
+    /* The PRODUCTION neighbour list of the last substep -- the very arrays the density pass wrote and the pressure
+     * and viscosity passes walked -- decoded to original ids (fields 4/5 above re-traverse the cells instead): */
+    SF_FIELD_LIST_COUNTS = 9,    /* uint32[n]     packed count per particle: fluid (14 bit) | wall X (6) | wall Y (6) | wall Z (6);
+                                                  0xffffffff = no list (capacity exceeded, the particle took the traversal path) */
+    SF_FIELD_LIST_IDS = 10,      /* uint32[sum]   fluid neighbours in LIST order (= the reference's traversal order A.6:
+                                                  cells z->y->x, ascending id inside a cell), concatenated in particle order */
+    SF_FIELD_LIST_TABLE_INDEX = 11 /* uint32[sum] kernel-table index min(trunc(sqrt(d2)*invStep), 10000) per list entry (A.2) */
 } sf_field;
 int sf_set_capture(sf_solver* s, int on);                         /* extra per-step stores for ACCEL */
+/* Entries per particle of the neighbour list the density pass builds (default 96; a rest-density particle has 32-40
+ * neighbours).  Particles with more take the cell-traversal path in all three passes: slower, same bits.  Before the
+ * first upload only. */
+int sf_set_list_capacity(sf_solver* s, int kmax);
 int sf_field_size(sf_solver* s, int field, uint64_t* bytes_out);
 int sf_download_field(sf_solver* s, int field, void* out, uint64_t bytes);
 int sf_grid_dims(sf_solver* s, int32_t n3[3]);                     /* Grid3D::setGrid EXE@0x14001ab20 */
+
+/* Diagnostics of the last substep: out = {substeps done, non-empty bricks, bricks whose halo did not fit the staging
+ * buffers (cumulative), particles whose list overflowed (cumulative), max fluid neighbour count, sum of fluid neighbour
+ * counts, particles without a list, particles resident on this rank}.  Synchronises. */
+int sf_diagnostics(sf_solver* s, uint64_t out[8]);
 
 /* ---- measurement ---------------------------------------------------------------------------- */
 /* Per-kernel CUDA-event timing on the launching stream.  sf_profile_enable(s, N): every N-th substep is timed

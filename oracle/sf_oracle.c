@@ -704,17 +704,19 @@ static int cmp_u32(const void* a, const void* b)
 /* Neighbour sets of the binning of the last step, evaluated on the positions that were binned.
  * Call it after sfo_collect_only() / before the positions move, or use sfo_neighbors_now(). */
 uint64_t sfo_neighbors(sfo_solver* s, uint32_t* counts, uint32_t* ids, uint64_t cap)
-{
+{ /* test helper (not part of the reference step): the A.6 traversal with the A.13 / A.11 range test, two parallel passes */
     if (!s->ready) sfo_make_ready(s);
     int rev = s->reversed;
     s->reversed = 0;
     collect_particles_to_cells(s);
-    uint64_t total = 0;
-    for (uint32_t p = 0; p < s->n; ++p) {
+    uint64_t* off = (uint64_t*)malloc(((size_t)s->n + 1) * sizeof(uint64_t));
+    omp_set_num_threads(s->nthreads > 0 ? s->nthreads : omp_get_num_procs());
+#pragma omp parallel for schedule(dynamic, 1024)
+    for (int64_t pi = 0; pi < (int64_t)s->n; ++pi) {
+        uint32_t p = (uint32_t)pi;
         const float* xp = s->pos + 3 * (size_t)p;
         int c[3];
         cell_coords(s, xp, c);
-        uint64_t first = total;
         uint32_t cnt = 0;
         FOR_NEIGHBOR_CELLS(s, c, {
             if (q == p) continue;
@@ -722,12 +724,34 @@ uint64_t sfo_neighbors(sfo_solver* s, uint32_t* counts, uint32_t* ids, uint64_t 
             float dx = xq[0] - xp[0], dy = xq[1] - xp[1], dz = xq[2] - xp[2];
             float d2 = (dx * dx + dy * dy) + dz * dz;
             if (d2 > s->P.kernelRadiusSqr) continue;
-            if (ids && total < cap) ids[total] = q;
-            total++; cnt++;
+            cnt++;
         })
-        if (ids && total <= cap) qsort(ids + first, cnt, 4, cmp_u32);
+        off[p + 1] = cnt;
         if (counts) counts[p] = cnt;
     }
+    off[0] = 0;
+    for (uint32_t p = 0; p < s->n; ++p) off[p + 1] += off[p];
+    uint64_t total = off[s->n];
+    if (ids && total <= cap) {
+#pragma omp parallel for schedule(dynamic, 1024)
+        for (int64_t pi = 0; pi < (int64_t)s->n; ++pi) {
+            uint32_t p = (uint32_t)pi;
+            const float* xp = s->pos + 3 * (size_t)p;
+            int c[3];
+            cell_coords(s, xp, c);
+            uint64_t o = off[p];
+            FOR_NEIGHBOR_CELLS(s, c, {
+                if (q == p) continue;
+                const float* xq = s->pos + 3 * (size_t)q;
+                float dx = xq[0] - xp[0], dy = xq[1] - xp[1], dz = xq[2] - xp[2];
+                float d2 = (dx * dx + dy * dy) + dz * dz;
+                if (d2 > s->P.kernelRadiusSqr) continue;
+                ids[o++] = q;
+            })
+            qsort(ids + off[p], (size_t)(off[p + 1] - off[p]), 4, cmp_u32);
+        }
+    }
+    free(off);
     s->reversed = rev;
     return total;
 }

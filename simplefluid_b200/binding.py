@@ -14,7 +14,7 @@ _LIB_PATH = os.path.join(_HERE, "lib", "libsf_b200.so")
 SCENES = {"SphereDrop": 0, "CubeDrop": 1, "Dambreak": 2, "DoubleDambreak": 3}  # Include/Common.h:52-58
 
 FIELD_DENSITY, FIELD_PRESSURE, FIELD_ACCEL, FIELD_CELL_INDEX, FIELD_NEIGHBOR_COUNT, FIELD_NEIGHBOR_IDS, \
-    FIELD_SORT_PERM, FIELD_TABLE_CUBIC_W, FIELD_TABLE_SPIKY_GRAD = range(9)
+    FIELD_SORT_PERM, FIELD_TABLE_CUBIC_W, FIELD_TABLE_SPIKY_GRAD, FIELD_LIST_COUNTS, FIELD_LIST_IDS, FIELD_LIST_TABLE_INDEX = range(12)
 
 EXPORTS = [
     "sf_params_default", "sf_params_set_resolution", "sf_params_update", "sf_scene_generate", "sf_build_tables",
@@ -27,7 +27,7 @@ EXPORTS = [
     "sf_comm_unique_id", "sf_comm_init", "sf_upload_particles_global", "sf_slab_info", "sf_download_owned",
     "sf_slab_plan", "sf_slab_rebalance", "sf_cell_layers", "sf_download_local", "sf_upload_local",
     "sf_snapshot_positions_async", "sf_snapshot_wait", "sf_checkpoint_write", "sf_checkpoint_read",
-    "sf_host_alloc", "sf_host_free",
+    "sf_host_alloc", "sf_host_free", "sf_diagnostics", "sf_set_list_capacity",
 ]
 
 
@@ -108,6 +108,7 @@ def library():
         "sf_snapshot_positions_async": [vp, vp], "sf_snapshot_wait": [vp],
         "sf_checkpoint_write": [vp, C.c_char_p, f32], "sf_checkpoint_read": [C.c_char_p, C.c_int, C.POINTER(vp), C.POINTER(f32)],
         "sf_host_alloc": [u64, C.POINTER(vp)], "sf_host_free": [vp],
+        "sf_diagnostics": [vp, vp], "sf_set_list_capacity": [vp, C.c_int],
         "sf_slab_plan": [vp, i32, i32, vp], "sf_slab_rebalance": [vp, i32, i32, vp], "sf_cell_layers": [PP, vp, u32, vp],
     }
     for name, argtypes in sig.items():
@@ -352,7 +353,8 @@ class SPHSolver:
     def field(self, field):
         nbytes = C.c_uint64(0)
         self._ck(self.L.sf_field_size(self.h, field, C.byref(nbytes)))
-        dtype = np.uint32 if field in (FIELD_CELL_INDEX, FIELD_NEIGHBOR_COUNT, FIELD_NEIGHBOR_IDS, FIELD_SORT_PERM) else np.float32
+        dtype = np.uint32 if field in (FIELD_CELL_INDEX, FIELD_NEIGHBOR_COUNT, FIELD_NEIGHBOR_IDS, FIELD_SORT_PERM, FIELD_LIST_COUNTS,
+                                       FIELD_LIST_IDS, FIELD_LIST_TABLE_INDEX) else np.float32
         out = np.empty(nbytes.value // 4, dtype)
         if nbytes.value:
             self._ck(self.L.sf_download_field(self.h, field, out.ctypes.data, nbytes.value))
@@ -374,6 +376,26 @@ class SPHSolver:
 
     def neighbors(self):
         return self.field(FIELD_NEIGHBOR_COUNT), self.field(FIELD_NEIGHBOR_IDS)
+
+    def productionLists(self):
+        """The neighbour list the density pass built and the force / viscosity passes walked, decoded:
+        (fluid counts[n] with -1 where the particle had no list, packed raw counts[n], ids[sum] in list order,
+        table indices[sum])."""
+        raw = self.field(FIELD_LIST_COUNTS)
+        nolist = raw == 0xFFFFFFFF
+        cnt = np.where(nolist, -1, raw & 16383).astype(np.int64)
+        return cnt, raw, self.field(FIELD_LIST_IDS), self.field(FIELD_LIST_TABLE_INDEX)
+
+    def setListCapacity(self, kmax):
+        self._ck(self.L.sf_set_list_capacity(self.h, int(kmax)))
+
+    def diagnostics(self):
+        out = (C.c_uint64 * 8)()
+        self._ck(self.L.sf_diagnostics(self.h, out))
+        keys = ("substeps", "bricks", "fallback_bricks", "fallback_particles", "nbr_max", "nbr_sum", "particles_without_list", "particles")
+        d = dict(zip(keys, (int(x) for x in out)))
+        d["nbr_mean"] = d["nbr_sum"] / max(d["particles"], 1)
+        return d
 
     # -- renderer hand-off / checkpoint
     def snapshotPositionsAsync(self, host_xyz):

@@ -716,6 +716,7 @@ int sf_create(const sf_params* p, int device, sf_solver** out)
     s->useGraph = std::getenv("SF_NO_GRAPH") == nullptr;
     if(const char* m = std::getenv("SF_LIST")) s->listTiled = std::strcmp(m, "ell") != 0;
     if(const char* m = std::getenv("SF_SORT")) s->countSort = std::strcmp(m, "radix") != 0;
+    if(const char* m = std::getenv("SF_KMAX")) s->kmax = std::min(std::max(std::atoi(m), 8), 16383);
     s->occDensity = std::max(s->occDensity, 1);
     s->occForce   = std::max(s->occForce, 1);
     s->occVisc    = std::max(s->occVisc, 1);
@@ -1159,6 +1160,14 @@ int sf_host_free(void* p)
     return SF_OK;
 }
 
+int sf_set_list_capacity(sf_solver* s, int kmax)
+{
+    if(!s || kmax < 8 || kmax > 16383) return SF_ERR_INVALID;
+    if(s->B.posA) return fail(s, SF_ERR_INVALID, "sf_set_list_capacity: call before the first upload");
+    s->kmax = kmax;
+    return SF_OK;
+}
+
 int sf_set_capture(sf_solver* s, int on)
 {
     if(!s) return SF_ERR_INVALID;
@@ -1214,6 +1223,47 @@ static int neighbor_lists_host(sf_solver* s, std::vector<uint32_t>& counts, std:
     return SF_OK;
 }
 
+// The production neighbour list of the last substep (what k_density_brick wrote and the two list walkers read),
+// decoded to original ids: counts = raw packed nbrCnt per original id (0xffffffff: no list, the particle took the
+// traversal path), ids / tabIdx = CSR in list order.
+static int production_lists_host(sf_solver* s, std::vector<uint32_t>& counts, std::vector<uint32_t>* ids, std::vector<uint32_t>* tabIdx)
+{
+    const uint32_t n = s->n;
+    counts.assign(n, 0);
+    if(ids) ids->clear();
+    if(tabIdx) tabIdx->clear();
+    if(n == 0) return SF_OK;
+    if(!s->B.keyB) return fail(s, SF_ERR_INVALID, "no substep has run yet");
+    if(s->params.bCorrectDensity) return fail(s, SF_ERR_INVALID, "production list download is not available with bCorrectDensity");
+    k_unpack_u32<<<cdiv(n, 256), 256, 0, s->stream>>>(s->B.nbrCnt, s->B.idA, reinterpret_cast<uint32_t*>(s->stage), n, 0u);
+    SF_CUDA(s, cudaMemcpyAsync(counts.data(), s->stage, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, s->stream));
+    SF_CUDA(s, cudaStreamSynchronize(s->stream));
+    if(!ids && !tabIdx) return SF_OK;
+    std::vector<unsigned long long> offset(static_cast<size_t>(n) + 1, 0);
+    for(uint32_t i = 0; i < n; ++i) offset[i + 1] = offset[i] + (counts[i] == kCntNoList ? 0u : (counts[i] & 16383u));
+    const unsigned long long total = offset[n];
+    if(ids) ids->assign(total, 0);
+    if(tabIdx) tabIdx->assign(total, 0);
+    if(total == 0) return SF_OK;
+    unsigned long long* dOff = nullptr;
+    uint32_t *          dIds = nullptr, *dIdx = nullptr;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&dOff), sizeof(unsigned long long) * (static_cast<size_t>(n) + 1));
+    if(e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&dIds), sizeof(uint32_t) * total);
+    if(e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&dIdx), sizeof(uint32_t) * total);
+    if(e == cudaSuccess) e = cudaMemcpyAsync(dOff, offset.data(), sizeof(unsigned long long) * (static_cast<size_t>(n) + 1), cudaMemcpyHostToDevice, s->stream);
+    if(e == cudaSuccess) {
+        k_list_decode<<<std::max<uint32_t>(1u, s->numBricks), kDecodeThreads, 0, s->stream>>>(s->B, s->P, dOff, dIds, dIdx);
+        if(ids) e = cudaMemcpyAsync(ids->data(), dIds, sizeof(uint32_t) * total, cudaMemcpyDeviceToHost, s->stream);
+        if(e == cudaSuccess && tabIdx) e = cudaMemcpyAsync(tabIdx->data(), dIdx, sizeof(uint32_t) * total, cudaMemcpyDeviceToHost, s->stream);
+    }
+    if(e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    cudaFree(dOff);
+    cudaFree(dIds);
+    cudaFree(dIdx);
+    SF_CUDA(s, e);
+    return SF_OK;
+}
+
 int sf_field_size(sf_solver* s, int field, uint64_t* bytes_out)
 {
     if(!s || !bytes_out) return SF_ERR_INVALID;
@@ -1223,6 +1273,7 @@ int sf_field_size(sf_solver* s, int field, uint64_t* bytes_out)
         case SF_FIELD_PRESSURE:
         case SF_FIELD_CELL_INDEX:
         case SF_FIELD_NEIGHBOR_COUNT:
+        case SF_FIELD_LIST_COUNTS:
         case SF_FIELD_SORT_PERM: *bytes_out = 4 * n; return SF_OK;
         case SF_FIELD_ACCEL: *bytes_out = 12 * n; return SF_OK;
         case SF_FIELD_TABLE_CUBIC_W:
@@ -1237,6 +1288,20 @@ int sf_field_size(sf_solver* s, int field, uint64_t* bytes_out)
             if(rc) return rc;
             uint64_t total = 0;
             for(uint32_t c : counts) total += c;
+            *bytes_out = 4 * total;
+            return SF_OK;
+        }
+        case SF_FIELD_LIST_IDS:
+        case SF_FIELD_LIST_TABLE_INDEX: {
+            int rc = require_ready(s);
+            if(rc) return rc;
+            SF_CUDA(s, cudaSetDevice(s->device));
+            SF_CUDA(s, cudaStreamSynchronize(s->stream));
+            std::vector<uint32_t> counts;
+            rc = production_lists_host(s, counts, nullptr, nullptr);
+            if(rc) return rc;
+            uint64_t total = 0;
+            for(uint32_t c : counts) total += c == kCntNoList ? 0u : (c & 16383u);
             *bytes_out = 4 * total;
             return SF_OK;
         }
@@ -1268,6 +1333,15 @@ int sf_download_field(sf_solver* s, int field, void* out, uint64_t bytes)
         std::memcpy(out, src.data(), 4ull * src.size());
         return SF_OK;
     }
+    if(field == SF_FIELD_LIST_COUNTS || field == SF_FIELD_LIST_IDS || field == SF_FIELD_LIST_TABLE_INDEX) {
+        std::vector<uint32_t> counts, ids, idx;
+        rc = production_lists_host(s, counts, field == SF_FIELD_LIST_IDS ? &ids : nullptr, field == SF_FIELD_LIST_TABLE_INDEX ? &idx : nullptr);
+        if(rc) return rc;
+        const std::vector<uint32_t>& src = field == SF_FIELD_LIST_IDS ? ids : (field == SF_FIELD_LIST_TABLE_INDEX ? idx : counts);
+        if(bytes < 4ull * src.size()) return fail(s, SF_ERR_INVALID, "buffer too small");
+        std::memcpy(out, src.data(), 4ull * src.size());
+        return SF_OK;
+    }
     const uint64_t need = (field == SF_FIELD_ACCEL ? 12ull : 4ull) * n;
     if(bytes < need) return fail(s, SF_ERR_INVALID, "buffer too small");
     if(n == 0) return SF_OK;
@@ -1290,6 +1364,40 @@ int sf_download_field(sf_solver* s, int field, void* out, uint64_t bytes)
     }
     SF_CUDA(s, cudaMemcpyAsync(out, s->stage, need, cudaMemcpyDeviceToHost, s->stream));
     SF_CUDA(s, cudaStreamSynchronize(s->stream));
+    return SF_OK;
+}
+
+// ---- diagnostics of the last substep ---------------------------------------------------------------
+int sf_diagnostics(sf_solver* s, uint64_t out[8])
+{
+    int rc = require_ready(s);
+    if(rc) return rc;
+    if(!out) return SF_ERR_INVALID;
+    SF_CUDA(s, cudaSetDevice(s->device));
+    rc = read_state(s);
+    if(rc) return rc;
+    const DevState& st = *s->hostState;
+    unsigned long long h[3] = { 0ull, 0ull, 0ull };
+    if(s->n && s->B.keyB && st.stepsDone) {
+        unsigned long long* d = nullptr;
+        SF_CUDA(s, cudaMalloc(reinterpret_cast<void**>(&d), sizeof(h)));
+        cudaError_t e = cudaMemsetAsync(d, 0, sizeof(h), s->stream);
+        if(e == cudaSuccess) {
+            k_nbr_stats<<<std::min<uint32_t>(cdiv(s->n, 256), s->numSMs * 8), 256, 0, s->stream>>>(s->B.nbrCnt, s->B.keyB, s->P, d);
+            e = cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, s->stream);
+        }
+        if(e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+        cudaFree(d);
+        SF_CUDA(s, e);
+    }
+    out[0] = st.stepsDone;
+    out[1] = st.brickCount;
+    out[2] = st.fallbackBricks;
+    out[3] = st.fallbackParticles;
+    out[4] = h[0];
+    out[5] = h[2];
+    out[6] = h[1];
+    out[7] = s->n;
     return SF_OK;
 }
 

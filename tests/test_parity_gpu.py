@@ -369,3 +369,164 @@ def test_async_position_snapshot(sf):
     assert exact(host.numpy(), expect)
     assert not exact(g.getParticles(), expect)
     g.close()
+
+
+# ---- round 2: the production neighbour list, and the BASELINE.json configs at full size -------------------------
+def _expected_table_index(pos0, ids_flat, counts, inv_step):
+    """min(trunc(sqrtf(d2) * invStep), 10000) per list entry, in separately rounded float32 (A.2, A.6)."""
+    owner = np.repeat(np.arange(len(counts), dtype=np.int64), counts)
+    d = pos0[ids_flat.astype(np.int64)] - pos0[owner]  # neighbour minus self, float32
+    d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+    t = np.sqrt(d2, dtype=np.float32) * np.float32(inv_step)
+    return np.minimum(t.astype(np.int64), 10000).astype(np.uint32)
+
+
+def check_production_list(gpu, pos0, ocnt, oids, inv_step, expect_nolist=None):
+    """Decodes nbrL / nbrCnt as k_density_brick wrote them (what k_force_brick / k_visc_brick walk) and compares with
+    the oracle's neighbour sets; entries must come in the reference's traversal order with the reference's table index."""
+    cnt, raw, ids, tab = gpu.productionLists()
+    nolist = cnt < 0
+    if expect_nolist is not None:
+        assert np.array_equal(nolist, expect_nolist), "particles without a list differ from the expectation"
+    has = ~nolist
+    assert np.array_equal(cnt[has], ocnt[has].astype(np.int64)), "production list lengths differ from the oracle's neighbour counts"
+    # oracle CSR restricted to the particles that have a list
+    ooff = np.concatenate([[0], np.cumsum(ocnt.astype(np.int64))])
+    keep = np.repeat(has, ocnt)
+    osel = oids[keep]
+    c = np.where(has, cnt, 0)
+    off = np.concatenate([[0], np.cumsum(c)])
+    assert len(ids) == off[-1] == len(osel)
+    # the list is in traversal order (cells z->y->x, ascending id per cell); as a SET it must equal the oracle's
+    owner = np.repeat(np.arange(len(c), dtype=np.int64), c)
+    order = np.lexsort((ids, owner))
+    assert np.array_equal(ids[order], osel), "production neighbour list differs from the oracle's sorted neighbour sets"
+    assert np.array_equal(tab, _expected_table_index(pos0, ids, c, inv_step)), "kernel-table indices in the list differ from A.2"
+    return int(has.sum()), ooff
+
+
+@pytest.mark.parametrize("scene,res", [("Dambreak", 24), ("SphereDrop", 40), ("DoubleDambreak", 61)])
+def test_production_neighbor_list_matches_oracle(sf, ob, scene, res):
+    gpu, orc, pos = make_pair(sf, ob, scene, res)
+    inv_step = float(sf.binding.build_tables(gpu.params)[2][2])
+    for _ in range(3):
+        x0 = orc.positions()
+        ocnt, oids = orc.neighbors()
+        assert orc.advance() == gpu.advanceFrame()
+        nlist, _ = check_production_list(gpu, x0, ocnt, oids, inv_step, expect_nolist=np.zeros(len(pos), bool))
+        assert nlist == len(pos)
+        d = gpu.diagnostics()
+        assert d["nbr_max"] == int(ocnt.max()) and d["nbr_sum"] == int(ocnt.astype(np.int64).sum()) and d["particles_without_list"] == 0
+    gpu.close()
+    orc.close()
+
+
+def test_production_list_capacity_overflow_falls_back(sf, ob):
+    """kmax = 24 on a lattice whose interior particles have 32 neighbours: those lists overflow, the particles take
+    the traversal path in all three passes (same bits), the others keep their lists."""
+    p = sf.default_params(24, "CubeDrop")
+    pos = sf.scene_generate(p)
+    gpu = sf.SPHSolver(p)
+    gpu.setListCapacity(24)
+    gpu.setParticles(pos)
+    gpu.generateBoundaryParticles(0)
+    gpu.setCapture(True)
+    gpu.makeReady()
+    orc = ob.Oracle(ob.default_params(24, "CubeDrop"), pos, boundary_seed=0)
+    inv_step = float(sf.binding.build_tables(p)[2][2])
+    for _ in range(3):
+        x0 = orc.positions()
+        ocnt, oids = orc.neighbors()
+        assert orc.advance() == gpu.advanceFrame()
+        check_step_fields(gpu, orc, ocnt, oids)
+        expect = ocnt > 24  # fluid neighbours only here: the cube is far from every wall
+        assert expect.any() and not expect.all()
+        check_production_list(gpu, x0, ocnt, oids, inv_step, expect_nolist=expect)
+        assert gpu.diagnostics()["particles_without_list"] == int(expect.sum())
+    gpu.close()
+    orc.close()
+
+
+def test_production_list_crowded(sf, ob):
+    """Ragged, crowded cells (> 64 neighbours, coincident points): list order and table index 0 entries."""
+    rng = np.random.default_rng(11)
+    p = sf.default_params(16, "CubeDrop")
+    h = p.kernelRadius
+    base = np.array([-0.2, -0.5, 0.1])
+    pos = (rng.random((700, 3)) * (3 * h) + base).astype(np.float32)  # ~26 per cell, ~110 neighbours in the middle
+    pos[10] = pos[11] = (base + 0.03 * h).astype(np.float32)            # coincident pair in a corner (few neighbours)
+    gpu, orc, _ = make_pair(sf, ob, "CubeDrop", 16, pos=pos)
+    inv_step = float(sf.binding.build_tables(p)[2][2])
+    ocnt, oids = orc.neighbors()
+    assert orc.advance() == gpu.advanceFrame()
+    cnt, raw, ids, tab = gpu.productionLists()
+    check_production_list(gpu, pos, ocnt, oids, inv_step)
+    assert (cnt < 0).any() and (cnt >= 0).any()  # some lists overflow the default capacity of 96, most do not
+    assert np.array_equal(cnt < 0, ocnt > 96)  # no walls near: the list holds fluid neighbours only
+    assert (tab == 0).any()  # the coincident pair
+    gpu.close()
+    orc.close()
+
+
+def _one_substep_full_size(sf, ob, scene, res, n_expect):
+    gpu, orc, pos = make_pair(sf, ob, scene, res)
+    assert len(pos) == n_expect
+    inv_step = float(sf.binding.build_tables(gpu.params)[2][2])
+    ocnt, oids = orc.neighbors()
+    assert orc.advance() == gpu.advanceFrame()
+    assert exact(gpu.cellIndex(), orc.cell_index()), "cell indices must be bit-exact"
+    check_production_list(gpu, pos, ocnt, oids, inv_step, expect_nolist=np.zeros(len(pos), bool))
+    gcnt = gpu.field(4)
+    assert exact(gcnt, ocnt)
+    del oids
+    for name, a, b in (("density", gpu.density(), orc.density()), ("pressure", gpu.pressure(), orc.pressure()),
+                       ("accel", gpu.accel(), orc.accel()), ("velocity", gpu.getVelocity(), orc.velocities()),
+                       ("position", gpu.getParticles(), orc.positions())):
+        e = rel_err(a, b)
+        assert e <= REL_TOL, f"{name}: relative error {e:.3e} > {REL_TOL}"
+        assert exact(a, b), f"{name}: within tolerance ({e:.3e}) but no longer bit-identical to the oracle"
+    d = gpu.diagnostics()
+    assert d["fallback_bricks"] == 0 and d["fallback_particles"] == 0
+    # a second substep: dt, positions, velocities, density
+    assert orc.advance() == gpu.advanceFrame()
+    assert exact(gpu.getParticles(), orc.positions()) and exact(gpu.getVelocity(), orc.velocities()) and exact(gpu.density(), orc.density())
+    gpu.close()
+    orc.close()
+
+
+def test_config3_double_dambreak_8m_vs_oracle(sf, ob):
+    """configs[2] at FULL size (DoubleDambreak res 161, 8,028,160 particles): cell index, production neighbour list,
+    rho, P, acceleration, v, x after one substep and x, v, rho after two -- bit for bit against the oracle."""
+    _one_substep_full_size(sf, ob, "DoubleDambreak", 161, 8_028_160)
+
+
+def test_config4_sphere_drop_16m_vs_oracle(sf, ob):
+    """configs[3] at FULL size (SphereDrop res 313, 16,054,752 particles, 30.7 M cells)."""
+    _one_substep_full_size(sf, ob, "SphereDrop", 313, 16_054_752)
+
+
+def test_developed_flow_vs_oracle(sf, ob):
+    """Parity on a DEVELOPED state (not the lattice): the GPU runs 1200 substeps of a res-64 dambreak (collapse, splash
+    against the far wall, rest density, ragged cells), the oracle takes over that state (positions + velocities) and
+    both advance 3 more substeps: every field bit-identical, production list included."""
+    p = sf.default_params(64, "Dambreak")
+    pos = sf.scene_generate(p)
+    g0 = sf.SPHSolver(p)
+    g0.setParticles(pos)
+    g0.generateBoundaryParticles(0)
+    g0.makeReady()
+    g0.advanceSteps(1200)
+    x, v = g0.getParticles(), g0.getVelocity()
+    d0 = g0.diagnostics()
+    g0.close()
+    assert d0["nbr_mean"] > 33 and x[:, 2].max() > 0.9  # the flow has developed
+    gpu, orc, _ = make_pair(sf, ob, "Dambreak", 64, pos=x, vel=v)
+    inv_step = float(sf.binding.build_tables(p)[2][2])
+    for _ in range(3):
+        x0 = orc.positions()
+        ocnt, oids = orc.neighbors()
+        assert orc.advance() == gpu.advanceFrame()
+        check_step_fields(gpu, orc, ocnt, oids)
+        check_production_list(gpu, x0, ocnt, oids, inv_step)
+    gpu.close()
+    orc.close()
