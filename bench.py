@@ -175,8 +175,12 @@ def cpu_oracle_run(scene, res, steps, warmup, threads=0):
 
 
 def base_config(workload, scene, res, n_total, n_gpus):
+    """Identical in both arms (--impl b200 / reference): what the workload IS.  How the GPU arm ran it (slab axis, ghost
+    fraction, settle time ...) goes into the top-level `run` object."""
     return {"workload": workload, "scene": scene, "resolution": res, "particles_total": int(n_total),
-            "particles_per_gpu": int(n_total // n_gpus), "boundary_seed": 0}
+            "particles_per_gpu": int(n_total // n_gpus), "grid_cells": int(res) ** 3, "boundary_seed": 0,
+            "parallelism": f"slab x{n_gpus} (one process per GPU)" if n_gpus > 1 else "single",
+            "l2": "inputs_exceed_l2" if (n_total // n_gpus) * 100 > 126e6 else "state_fits_l2_not_flushed"}
 
 
 def run_reference(args):
@@ -403,22 +407,19 @@ def run_b200(args):
                "sample": f"{scene} res {res} ({cn} particles, same configuration) x {csteps} substeps from the initial lattice in {secs:.1f} s, OpenMP {cores} threads"}
 
     config = base_config(args.workload, scene, res, n_total, n_gpus)
-    config.update({
-        "grid_cells": int(np.prod(gpu.gridDims())),
-        "state": f"developed flow: {args.warmup} warm-up + {args.steps} at-rest + {args.settle} settle substeps before the timed region",
-        "settle_substeps": args.settle, "settle_wall_s": round(t_settle, 2),
-        "parallelism": (f"{'yz'[slab_axis - 1]}-slab x{n_gpus} (3-layer ghost halo, 1 NCCL exchange + 1 allreduce per substep)" if multi else "single"),
-        "l2": "inputs_exceed_l2" if n * 100 > 126e6 else "state_fits_l2_not_flushed",
-    })
+    assert config["grid_cells"] == int(np.prod(gpu.gridDims()))
+    run = {"state": f"developed flow: {args.warmup} warm-up + {args.steps} at-rest + {args.settle} settle substeps before the timed region",
+           "settle_substeps": args.settle, "settle_wall_s": round(t_settle, 2)}
     if multi:
-        config.update({"ghost_fraction": round(ghost_frac, 4), "owned_max_over_mean": round(own_max / (total_particles / n_gpus), 4),
-                       "slab_thickness_min_layers": int(thick_min), "numa_node_rank0": numa})
+        run.update({"slab_axis": "xyz"[slab_axis], "ghost_layers_per_side": 3, "ghost_fraction": round(ghost_frac, 4),
+                    "owned_max_over_mean": round(own_max / (total_particles / n_gpus), 4),
+                    "slab_thickness_min_layers": int(thick_min), "numa_node_rank0": numa})
     line = {
         "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": n_gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": config,
         "value_at_rest": value_rest, "ms_per_step_at_rest": ms_rest / args.steps,
-        "flow": {"developed": diag, "at_rest": diag_rest},
+        "run": run, "flow": {"developed": diag, "at_rest": diag_rest},
         "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "api": e2e_api},
         "gpu_launches": int(launches),

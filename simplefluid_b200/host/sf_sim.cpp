@@ -1,6 +1,8 @@
 // sf_sim -- headless driver: runs a scene through the Simulator facade and optionally dumps one binary frame file
 // per 1/30 s frame (header: "SFF1", uint32 n, float simTime; then n x 3 fp32 positions in original particle order).
-//   sf_sim --scene Dambreak --resolution 24 --stop-time 0.5 [--dump-prefix out/frame] [--seed 0]
+//   sf_sim --scene Dambreak --resolution 24 --stop-time 0.5 [--dump-prefix out/frame] [--seed 0] [--pause-frame K]
+// --pause-frame K: stop() after frame K, then startSimulation() again -- the GUI's Stop / Start buttons; the flow
+// continues where it stopped (Source/Simulator.cpp:22-30,66-69).
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -14,6 +16,7 @@ int main(int argc, char** argv)
     std::string scene = "Dambreak", dump;
     float       resolution = 24.f, stopTime = 0.5f;
     uint32_t    seed = 0;
+    unsigned    pauseFrame = 0;
     for(int i = 1; i + 1 < argc; i += 2) {
         const std::string k = argv[i];
         if(k == "--scene") scene = argv[i + 1];
@@ -21,6 +24,7 @@ int main(int argc, char** argv)
         else if(k == "--stop-time") stopTime = static_cast<float>(std::atof(argv[i + 1]));
         else if(k == "--dump-prefix") dump = argv[i + 1];
         else if(k == "--seed") seed = static_cast<uint32_t>(std::atoi(argv[i + 1]));
+        else if(k == "--pause-frame") pauseFrame = static_cast<unsigned>(std::atoi(argv[i + 1]));
     }
     const char* names[4] = { "SphereDrop", "CubeDrop", "Dambreak", "DoubleDambreak" };
     int         sid      = -1;
@@ -41,6 +45,7 @@ int main(int argc, char** argv)
         unsigned frames = 0;
         sim.frameFinished = [&] {
             ++frames;
+            if(pauseFrame && frames == pauseFrame) sim.stop();
             if(dump.empty()) return;
             auto&       x = sim.solver().getParticles();
             char        name[512];
@@ -59,6 +64,10 @@ int main(int argc, char** argv)
         const auto     t0 = std::chrono::steady_clock::now();
         sim.startSimulation();
         while(sim.isRunning()) std::this_thread::sleep_for(std::chrono::milliseconds(2));
+        if(pauseFrame && sim.simTime() < stopTime) {
+            sim.startSimulation();
+            while(sim.isRunning()) std::this_thread::sleep_for(std::chrono::milliseconds(2));
+        }
         const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         auto&        x    = sim.solver().getParticles();
         double       cx = 0, cy = 0, cz = 0;

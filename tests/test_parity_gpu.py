@@ -387,7 +387,9 @@ def check_production_list(gpu, pos0, ocnt, oids, inv_step, expect_nolist=None):
     cnt, raw, ids, tab = gpu.productionLists()
     nolist = cnt < 0
     if expect_nolist is not None:
-        assert np.array_equal(nolist, expect_nolist), "particles without a list differ from the expectation"
+        bad = np.flatnonzero(nolist != expect_nolist)
+        assert len(bad) == 0, (f"particles without a list differ from the expectation: {len(bad)} of {len(cnt)}; first {bad[:8]}, "
+                               f"oracle counts {ocnt[bad[:8]]}, list counts {cnt[bad[:8]]}, raw {raw[bad[:8]]}")
     has = ~nolist
     assert np.array_equal(cnt[has], ocnt[has].astype(np.int64)), "production list lengths differ from the oracle's neighbour counts"
     # oracle CSR restricted to the particles that have a list
