@@ -134,9 +134,15 @@ int sf_host_free(void* p);
  * The solver may keep stepping; host_xyz is valid after sf_snapshot_wait. */
 int sf_snapshot_positions_async(sf_solver* s, float* host_xyz);
 int sf_snapshot_wait(sf_solver* s);
-/* {params, wall particles, simulated time, positions, velocities}; a restarted run continues bit-identically. */
+/* {params, wall particles, simulated time, positions, velocities}; a restarted run continues bit-identically.
+ * A slab run (sf_comm_init) writes one part per rank, `<path>.<rank>`: the particles that rank owns with their global
+ * ids; every rank calls sf_checkpoint_write with the same path.  sf_checkpoint_read restores either form on one GPU;
+ * sf_checkpoint_read_slab restores it as rank `rank` of `nranks` (any number of ranks, not necessarily the number that
+ * wrote it: the cut planes are re-planned, results do not depend on them).  Counts in the file are validated against
+ * its size; a truncated or inconsistent file gives SF_ERR_INVALID. */
 int sf_checkpoint_write(sf_solver* s, const char* path, float sim_time);
 int sf_checkpoint_read(const char* path, int device, sf_solver** out, float* sim_time);
+int sf_checkpoint_read_slab(const char* path, int device, int rank, int nranks, const void* nccl_unique_id128, sf_solver** out, float* sim_time);
 
 /* ---- parity / inspection fields (state of the LAST substep, original particle order) -------- */
 typedef enum sf_field {
@@ -194,8 +200,17 @@ int sf_comm_init(sf_solver* s, int rank, int nranks, const void* id128);
  * of its own z-range of cell layers, cut so that counts balance. */
 int sf_upload_particles_global(sf_solver* s, const float* pos_xyz, const float* vel_xyz, uint32_t n_global);
 int sf_slab_info(sf_solver* s, int32_t* z_begin, int32_t* z_end, uint32_t* n_owned, uint32_t* n_ghost);
-/* Owned particles with their global (original) ids. */
+/* Slow axis of the cell key = the axis the slabs are cut along: 2 = z (single GPU, and slab runs by default), 1 = y. */
+int sf_slab_axis(sf_solver* s, int32_t* axis_out);
+/* Owned particles with their global (original) ids, compacted on the device; any of ids / pos_xyz / vel_xyz may be
+ * NULL, at most cap particles are written, *n_out = the owned count.  Order: unspecified (the ids say who is who). */
 int sf_download_owned(sf_solver* s, uint32_t* ids, float* pos_xyz, float* vel_xyz, uint32_t cap, uint32_t* n_out);
+/* Host-buffer step of a slab run (the multi-GPU counterpart of sf_step_host, what bench.py's e2e leg times at N > 1):
+ * upload this rank's m_in OWNED particles {id, position, velocity} -- the resident copies are dropped, the ghost
+ * particles of the coming substep stay on the device (they belong to the neighbours and arrived with the last
+ * exchange) -- one substep incl. halo exchange and migration, download the particles this rank owns afterwards
+ * (*m_out, at most cap written).  SF_ERR_DOMAIN when an uploaded particle lies outside the box or this rank's layers. */
+int sf_step_host_owned(sf_solver* s, uint32_t* ids, float* pos_xyz, float* vel_xyz, uint32_t m_in, uint32_t cap, uint32_t* m_out, float* dt_out);
 /* Raw resident state of this rank (float4 positions/velocities + ids, all slots) to / from host buffers. */
 int sf_download_local(sf_solver* s, float* pos4, float* vel4, uint32_t* ids, uint32_t cap, uint32_t* n_out);
 int sf_upload_local(sf_solver* s, const float* pos4, const float* vel4, const uint32_t* ids, uint32_t n);

@@ -285,11 +285,13 @@ static uint32_t mt_next(mt19937* g)
     y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
     return y;
 }
-/* generate_canonical<float,24>: one 32-bit draw -> [0,1) with 24 bits */
-static float mt_canon(mt19937* g) { return (float)(mt_next(g) >> 8) * (1.0f / 16777216.0f); }
+/* MSVC std::generate_canonical<float,24> over mt19937, EXE@0x1400101a0: k = max(1, ceil(24 / log2(2^32))) = 1 draw;
+ * ans = 0 + (float)(uint32 draw) * 1.0f (cvtsi2ss of the zero-extended draw: round to nearest);
+ * return ans / (1.0f * 4294967296.0f).  May return exactly 1.0f. */
+static float mt_canon(mt19937* g) { return (float)mt_next(g) / 4294967296.0f; }
 
 void sfo_generate_boundary(sfo_solver* s, uint32_t seed)
-{ /* EXE@0x140016d80 (A.4) */
+{ /* EXE@0x140016d80 (A.4); roles of the three draws per wall: EXE@0x14001705a-0x1400172e0 */
     const sfo_params* P = &s->P;
     mt19937 gen;
     mt_seed(&gen, seed);
@@ -308,21 +310,34 @@ void sfo_generate_boundary(sfo_solver* s, uint32_t seed)
     for (int i = 0; i < nA; ++i)
         for (int j = 0; j < nA; ++j)
             for (int k = 0; k < nB; ++k) {
-                float ti = base + (float)i * sp;
-                float tj = base + (float)j * sp;
-                float depth = (float)k * sp + r;
-                for (int w = 0; w < 6; ++w) {
-                    float a = mt_canon(&gen) * (hi - lo) + lo;
-                    float b = mt_canon(&gen) * (hi - lo) + lo;
-                    float c = mt_canon(&gen) * (lo - 0.0f) + 0.0f;
-                    int axis = w >> 1, upper = w & 1;
-                    float nrm = upper ? (P->boxMax[axis] + depth) + c : (P->boxMin[axis] - depth) + c;
-                    float t0 = ti + b, t1 = tj + a;
-                    float* o = s->bnd[w] + 3 * (size_t)s->nbnd[w]++;
-                    if (axis == 0) { o[0] = nrm; o[1] = t0; o[2] = t1; }
-                    else if (axis == 1) { o[0] = t0; o[1] = nrm; o[2] = t1; }
-                    else { o[0] = t0; o[1] = t1; o[2] = nrm; }
-                }
+                float ti = base + (float)i * sp;   /* xmm15: outer loop */
+                float tj = base + (float)j * sp;   /* xmm11: middle loop */
+                float depth = (float)k * sp + r;   /* xmm8 */
+                float u[3], *o;
+                /* LX 0x14001705a: jit, jit, depth-jit */
+                u[0] = mt_canon(&gen) * (hi - lo) + lo; u[1] = mt_canon(&gen) * (hi - lo) + lo; u[2] = mt_canon(&gen) * (lo - 0.0f) + 0.0f;
+                o = s->bnd[0] + 3 * (size_t)s->nbnd[0]++;
+                o[0] = (P->boxMin[0] - depth) + u[2]; o[1] = u[1] + ti; o[2] = u[0] + tj;
+                /* UX 0x1400170c7 */
+                u[0] = mt_canon(&gen) * (hi - lo) + lo; u[1] = mt_canon(&gen) * (hi - lo) + lo; u[2] = mt_canon(&gen) * (lo - 0.0f) + 0.0f;
+                o = s->bnd[1] + 3 * (size_t)s->nbnd[1]++;
+                o[0] = u[2] + (depth + P->boxMax[0]); o[1] = u[1] + ti; o[2] = u[0] + tj;
+                /* LY 0x140017133: jit, depth-jit, jit */
+                u[0] = mt_canon(&gen) * (hi - lo) + lo; u[1] = mt_canon(&gen) * (lo - 0.0f) + 0.0f; u[2] = mt_canon(&gen) * (hi - lo) + lo;
+                o = s->bnd[2] + 3 * (size_t)s->nbnd[2]++;
+                o[0] = u[2] + ti; o[1] = (P->boxMin[1] - depth) + u[1]; o[2] = u[0] + tj;
+                /* UY 0x1400171a0 */
+                u[0] = mt_canon(&gen) * (hi - lo) + lo; u[1] = mt_canon(&gen) * (lo - 0.0f) + 0.0f; u[2] = mt_canon(&gen) * (hi - lo) + lo;
+                o = s->bnd[3] + 3 * (size_t)s->nbnd[3]++;
+                o[0] = u[2] + ti; o[1] = (depth + P->boxMax[1]) + u[1]; o[2] = u[0] + tj;
+                /* LZ 0x14001720c: depth-jit, jit, jit */
+                u[0] = mt_canon(&gen) * (lo - 0.0f) + 0.0f; u[1] = mt_canon(&gen) * (hi - lo) + lo; u[2] = mt_canon(&gen) * (hi - lo) + lo;
+                o = s->bnd[4] + 3 * (size_t)s->nbnd[4]++;
+                o[0] = u[2] + ti; o[1] = u[1] + tj; o[2] = (P->boxMin[2] - depth) + u[0];
+                /* UZ 0x140017278 */
+                u[0] = mt_canon(&gen) * (lo - 0.0f) + 0.0f; u[1] = mt_canon(&gen) * (hi - lo) + lo; u[2] = mt_canon(&gen) * (hi - lo) + lo;
+                o = s->bnd[5] + 3 * (size_t)s->nbnd[5]++;
+                o[0] = u[2] + ti; o[1] = u[1] + tj; o[2] = (depth + P->boxMax[2]) + u[0];
             }
 }
 

@@ -28,6 +28,7 @@ EXPORTS = [
     "sf_slab_plan", "sf_slab_rebalance", "sf_cell_layers", "sf_download_local", "sf_upload_local",
     "sf_snapshot_positions_async", "sf_snapshot_wait", "sf_checkpoint_write", "sf_checkpoint_read",
     "sf_host_alloc", "sf_host_free", "sf_diagnostics", "sf_set_list_capacity",
+    "sf_slab_axis", "sf_step_host_owned", "sf_checkpoint_read_slab",
 ]
 
 
@@ -109,6 +110,9 @@ def library():
         "sf_checkpoint_write": [vp, C.c_char_p, f32], "sf_checkpoint_read": [C.c_char_p, C.c_int, C.POINTER(vp), C.POINTER(f32)],
         "sf_host_alloc": [u64, C.POINTER(vp)], "sf_host_free": [vp],
         "sf_diagnostics": [vp, vp], "sf_set_list_capacity": [vp, C.c_int],
+        "sf_slab_axis": [vp, C.POINTER(i32)],
+        "sf_step_host_owned": [vp, vp, vp, vp, u32, u32, C.POINTER(u32), C.POINTER(f32)],
+        "sf_checkpoint_read_slab": [C.c_char_p, C.c_int, C.c_int, C.c_int, vp, C.POINTER(vp), C.POINTER(f32)],
         "sf_slab_plan": [vp, i32, i32, vp], "sf_slab_rebalance": [vp, i32, i32, vp], "sf_cell_layers": [PP, vp, u32, vp],
     }
     for name, argtypes in sig.items():
@@ -383,7 +387,7 @@ class SPHSolver:
         table indices[sum])."""
         raw = self.field(FIELD_LIST_COUNTS)
         nolist = raw == 0xFFFFFFFF
-        cnt = np.where(nolist, -1, raw & 16383).astype(np.int64)
+        cnt = np.where(nolist, np.int64(-1), (raw & 16383).astype(np.int64))
         return cnt, raw, self.field(FIELD_LIST_IDS), self.field(FIELD_LIST_TABLE_INDEX)
 
     def setListCapacity(self, kmax):
@@ -443,6 +447,43 @@ class SPHSolver:
         v = np.empty((n.value, 3), np.float32)
         self._ck(self.L.sf_download_owned(self.h, ids.ctypes.data, x.ctypes.data, v.ctypes.data, n.value, C.byref(n)))
         return ids, x, v
+
+    def downloadOwnedInto(self, ids, pos, vel):
+        """Owned particles into caller-provided (ideally pinned) buffers; returns the count."""
+        n = C.c_uint32(0)
+        self._ck(self.L.sf_download_owned(self.h, _ptr(ids), _ptr(pos), _ptr(vel), ids.shape[0], C.byref(n)))
+        if n.value > ids.shape[0]:
+            raise SFError(-1, f"buffers hold {ids.shape[0]} particles, the rank owns {n.value}")
+        return n.value
+
+    def stepHostOwned(self, ids, pos, vel, m):
+        """sf_step_host_owned: upload the m owned particles in the buffers, one substep, download the new owned set
+        into the same buffers; returns its size."""
+        out, dt = C.c_uint32(0), C.c_float(0)
+        self._ck(self.L.sf_step_host_owned(self.h, _ptr(ids), _ptr(pos), _ptr(vel), int(m), ids.shape[0], C.byref(out), C.byref(dt)))
+        if out.value > ids.shape[0]:
+            raise SFError(-1, f"buffers hold {ids.shape[0]} particles, the rank owns {out.value}")
+        self.last_dt = dt.value
+        return out.value
+
+    def slabAxis(self):
+        a = C.c_int32(2)
+        self._ck(self.L.sf_slab_axis(self.h, C.byref(a)))
+        return a.value
+
+    @classmethod
+    def fromCheckpointSlab(cls, path, device, rank, nranks, unique_id_bytes):
+        L = library()
+        h, t = C.c_void_p(), C.c_float(0)
+        buf = C.create_string_buffer(bytes(unique_id_bytes), 128) if unique_id_bytes is not None else None
+        rc = L.sf_checkpoint_read_slab(str(path).encode(), device, rank, nranks, buf, C.byref(h), C.byref(t))
+        if rc:
+            raise SFError(rc, (L.sf_last_error(None) or b"").decode())
+        self = cls.__new__(cls)
+        self.L, self.h = L, h
+        self.params = SFParams()
+        L.sf_get_params(h, C.byref(self.params))
+        return self, t.value
 
     def localSlots(self):
         n = C.c_uint32(0)

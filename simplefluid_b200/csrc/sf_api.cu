@@ -10,6 +10,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <vector>
 #include "sf_internal.h"
@@ -100,7 +102,12 @@ struct sf_solver {
         uint64_t             exchangedParticles = 0;
         double               tWaitPack = 0, tPost = 0, tFront = 0; // host seconds: waiting for the table / posting the exchange / enqueueing
         uint64_t             steps = 0;
+        // global dt: the all-reduce of max |v|^2 runs on the communication stream behind the exchange and is awaited
+        // only before the force pass of the next substep (dtReduced: evDt covers the current maxv2Bits)
+        cudaEvent_t          evInterior = nullptr, evDt = nullptr;
+        bool                 dtReduced = false;
     } slab;
+    uint32_t *ownCounters = nullptr, *hostOwnCounters = nullptr; // device / pinned: sf_download_owned, sf_step_host_owned
 
     // measurement
     bool                      profiling = false; // the substep being enqueued is timed kernel by kernel
@@ -303,6 +310,7 @@ int ensure_particle_capacity(sf_solver* s, uint32_t n, uint32_t preserve = 0)
 }
 
 int slab_exchange(sf_solver* s, uint32_t n, uint32_t nSlots);
+int slab_global_dt(sf_solver* s);
 
 // One reference substep (advanceFrame, EXE@0x140016810) as a launch sequence on the solver's stream.
 // n = live particles, nSlots >= n = slots of the A arrays to sort (slab mode keeps last step's dead ghost slots).
@@ -317,14 +325,14 @@ int enqueue_substep_launches(sf_solver* s, const float* velHostXYZ = nullptr)
     const uint32_t  n      = s->n;
     const uint32_t  nSlots = slab ? s->nSlots : n;
     const uint32_t  gridN  = cdiv(n, 256);
-    if(slab) { // global dt: max |v|^2 over all slabs (uint32 order == float order for non-negative floats)
-        NcclApi& nc = nccl_api();
-        if(nc.AllReduce(B.state->maxv2Bits, B.state->maxv2Bits, 2, ncclUint32, ncclMax, s->slab.comm, st) != ncclSuccess)
-            return fail(s, SF_ERR_COMM, "ncclAllReduce(max |v|^2) failed");
-    }
+    // Slab mode: dt needs max |v|^2 over ALL slabs (uint32 order == float order for non-negative floats).  The
+    // all-reduce was issued on the communication stream behind the previous substep's exchange (slab_exchange) and is
+    // awaited only before the force pass: sorting and the density pass need no dt, so the skew between ranks -- every
+    // rank would otherwise wait here for the slowest one to finish integrating -- hides behind them.
+    const bool splitClock = velHostXYZ != nullptr || slab;
     {
         LaunchScope ls(s, K_BEGIN);
-        k_begin_step<<<1, 1, 0, st>>>(B.state, P, velHostXYZ ? kBeginResets : kBeginAll);
+        k_begin_step<<<1, 1, 0, st>>>(B.state, P, splitClock ? kBeginResets : kBeginAll);
     }
     if(nSlots == 0 && !slab) {
         if(velHostXYZ) k_begin_step<<<1, 1, 0, st>>>(B.state, P, kBeginClock);
@@ -422,6 +430,12 @@ int enqueue_substep_launches(sf_solver* s, const float* velHostXYZ = nullptr)
             k_gather_vel_host<<<gridN, 256, 0, st>>>(velHostXYZ, B.idB, B.velB, n, B.state);
             k_begin_step<<<1, 1, 0, st>>>(B.state, P, kBeginClock);
         }
+    }
+    if(slab) {
+        const int rc = slab_global_dt(s);
+        if(rc) return rc;
+    }
+    if(n) {
         {
             LaunchScope ls(s, K_FORCE);
             k_force_brick<<<std::min<uint32_t>(pairGrid, s->numSMs * s->occForce), kBrickThreads, kSmemPair, st>>>(B, P);
@@ -524,6 +538,25 @@ int slab_configure_window(sf_solver* s)
     return SF_OK;
 }
 
+// dt of a slab substep (A.5 on the global max |v|^2) right before the force pass.  Normally the all-reduce is already
+// in flight on the communication stream (issued by the previous substep's slab_exchange); after makeReady or a host
+// upload it runs in-stream.  k_begin_step(kBeginClock) also resets the other max slot, which the integrate kernel of
+// THIS substep accumulates into -- hence it must run after the all-reduce (in place on both slots) and before
+// k_visc_brick, which the stream order guarantees.
+int slab_global_dt(sf_solver* s)
+{
+    sf_solver::Slab& L = s->slab;
+    if(L.dtReduced) {
+        SF_CUDA(s, cudaStreamWaitEvent(s->stream, L.evDt, 0));
+    } else if(nccl_api().AllReduce(s->B.state->maxv2Bits, s->B.state->maxv2Bits, 2, ncclUint32, ncclMax, L.comm, s->stream) != ncclSuccess) {
+        return fail(s, SF_ERR_COMM, "ncclAllReduce(max |v|^2) failed");
+    }
+    L.dtReduced = false;
+    LaunchScope ls(s, K_BEGIN);
+    k_begin_step<<<1, 1, 0, s->stream>>>(s->B.state, s->P, kBeginClock);
+    return SF_OK;
+}
+
 // Tail of a slab substep: integrate edge bricks, exchange them while the interior bricks integrate.
 int slab_exchange(sf_solver* s, uint32_t n, uint32_t nSlots)
 {
@@ -545,6 +578,7 @@ int slab_exchange(sf_solver* s, uint32_t n, uint32_t nSlots)
         const uint32_t g = std::min<uint32_t>(pairGrid, s->numSMs * s->occVisc);
         k_visc_brick<<<g > 32 ? g - 4 : g, kBrickThreads, kSmemPair, cs>>>(B, P, 2);
     }
+    SF_CUDA(s, cudaEventRecord(L.evInterior, cs));
     // ---- communication stream
     const int hasLower = L.rank > 0, hasUpper = L.rank < L.nranks - 1;
     SF_CUDA(s, cudaStreamWaitEvent(ms, L.evEdge, 0));
@@ -602,6 +636,13 @@ int slab_exchange(sf_solver* s, uint32_t n, uint32_t nSlots)
     if(recvHi) k_slab_unpack<<<cdiv(recvHi, 256), 256, 0, ms>>>(L.recvHi, recvHi, B.posA + n + recvLo, B.velA + n + recvLo, B.idA + n + recvLo);
     SF_CUDA(s, cudaEventRecord(L.evExchanged, ms));
     SF_CUDA(s, cudaStreamWaitEvent(cs, L.evExchanged, 0));
+    // max |v|^2 of this substep is complete once the interior bricks are integrated: reduce it over the ranks on the
+    // communication stream; the next substep waits for it only before its force pass (slab_global_dt)
+    SF_CUDA(s, cudaStreamWaitEvent(ms, L.evInterior, 0));
+    if(nc.AllReduce(B.state->maxv2Bits, B.state->maxv2Bits, 2, ncclUint32, ncclMax, L.comm, ms) != ncclSuccess)
+        return fail(s, SF_ERR_COMM, "ncclAllReduce(max |v|^2) failed");
+    SF_CUDA(s, cudaEventRecord(L.evDt, ms));
+    L.dtReduced = true;
     SF_CUDA(s, cudaGetLastError());
     // ---- bookkeeping for the next substep: live = my integrated particles + received; dead = this substep's ghosts
     s->nSlots = n + recvLo + recvHi;
@@ -691,7 +732,8 @@ int sf_create(const sf_params* p, int device, sf_solver** out)
     SF_CUDA(nullptr, cudaGetDeviceProperties(&prop, device));
     if(prop.major < 10) return fail(nullptr, SF_ERR_CUDA, std::string("device ") + prop.name + " is not sm_100 class; kernels are built for sm_100a only");
     SF_CUDA(nullptr, cudaSetDevice(device));
-    sf_solver* s = new sf_solver();
+    sf_solver* s = new(std::nothrow) sf_solver();
+    if(!s) return fail(nullptr, SF_ERR_OOM, "sf_create: out of host memory");
     s->params    = *p;
     s->device    = device;
     s->numSMs    = prop.multiProcessorCount;
@@ -760,15 +802,20 @@ void sf_destroy(sf_solver* s)
             std::fprintf(stderr, "[sf slab rank %d] %llu substeps: host wait for edge+pack+allgather %.3f ms/step, post exchange %.3f ms/step, exchanged %.1f particles/step, %llu capacity regrowths, axis %c\n",
                          L.rank, (unsigned long long)L.steps, L.tWaitPack / L.steps * 1e3, L.tPost / L.steps * 1e3, double(L.exchangedParticles) / L.steps,
                          (unsigned long long)L.regrowths, s->axisS == 1 ? 'y' : 'z');
+        if(L.commStream) cudaStreamSynchronize(L.commStream); // the last substep's dt all-reduce may still be in flight
         if(L.comm && nccl_api().CommDestroy) nccl_api().CommDestroy(L.comm);
         cudaFree(L.sendLo); cudaFree(L.sendHi); cudaFree(L.recvLo); cudaFree(L.recvHi);
         cudaFree(L.layerStart); cudaFree(L.counters); cudaFree(L.row); cudaFree(L.table);
         if(L.hostTable) cudaFreeHost(L.hostTable);
         if(L.evEdge) cudaEventDestroy(L.evEdge);
         if(L.evExchanged) cudaEventDestroy(L.evExchanged);
+        if(L.evInterior) cudaEventDestroy(L.evInterior);
+        if(L.evDt) cudaEventDestroy(L.evDt);
         if(L.commStream) cudaStreamDestroy(L.commStream);
     }
     if(s->hostState) cudaFreeHost(s->hostState);
+    cudaFree(s->ownCounters);
+    if(s->hostOwnCounters) cudaFreeHost(s->hostOwnCounters);
     if(s->timerA) cudaEventDestroy(s->timerA);
     if(s->timerB) cudaEventDestroy(s->timerB);
     if(s->ownStream) cudaStreamDestroy(s->ownStream);
@@ -963,6 +1010,7 @@ int sf_make_ready(sf_solver* s)
     }
     SF_CUDA(s, cudaStreamSynchronize(s->stream));
     SF_CUDA(s, cudaGetLastError());
+    s->slab.dtReduced = false; // max |v|^2 was recomputed locally: the first substep all-reduces it in-stream
     s->ready = true;
     return SF_OK;
 }
@@ -1515,81 +1563,209 @@ int sf_snapshot_wait(sf_solver* s)
 }
 
 // ---- checkpoint / restart ------------------------------------------------
-// State = {params, wall particle sets, simulated time, positions, velocities in original order}.  Restarting
-// from it continues bit-identically: dt is recomputed from max |v|^2 (an exact max), and the sort re-derives
-// the cell order from positions and ids alone.
+// State = {params, wall particle sets, simulated time, particles {id, position, velocity}}.  A single-GPU run
+// writes one file (ids implicit: original order); a slab run writes one part per rank, `<path>.<rank>`, holding the
+// particles that rank owns with their global ids.  Restarting continues bit-identically: dt is recomputed from max
+// |v|^2 (an exact max), the sort re-derives the cell order from positions and ids alone, and the result of a slab
+// run does not depend on where the cut planes lie -- so a checkpoint may be restarted on ANY number of ranks
+// (sf_checkpoint_read: one GPU; sf_checkpoint_read_slab: a rank of a slab run), the cut planes are re-planned.
 namespace
 {
 struct CheckpointHeader {
-    char     magic[8]; // "SFCKPT1\0"
+    char     magic[8]; // "SFCKPT2\0"
     uint32_t paramsBytes, n, wallCount[6];
     float    simTime;
+    uint32_t hasWalls;   // 0: written before the wall particles were generated / set
+    uint32_t hasIds;     // 1: a part of a slab checkpoint, ids follow the velocities
+    uint32_t part, parts; // this part / number of parts
+    uint64_t nGlobal;
 };
+
+struct CheckpointData {
+    sf_params             p{};
+    std::vector<float>    walls[6], x, v; // x, v: global arrays in id order once all parts are merged
+    bool                  hasWalls = false;
+    float                 simTime = 0.f;
+    uint64_t              nGlobal = 0;
+};
+
+long file_size(FILE* f)
+{
+    const long at = std::ftell(f);
+    std::fseek(f, 0, SEEK_END);
+    const long sz = std::ftell(f);
+    std::fseek(f, at, SEEK_SET);
+    return sz;
+}
+
+// reads one file (whole checkpoint or one part) and merges its particles into d; returns false on any inconsistency
+bool checkpoint_read_file(const std::string& path, CheckpointData& d, uint32_t expectPart, uint32_t* partsOut, std::vector<unsigned char>* seen)
+{
+    FILE* f = std::fopen(path.c_str(), "rb");
+    if(!f) return false;
+    CheckpointHeader h{};
+    sf_params        p{};
+    bool ok = std::fread(&h, sizeof(h), 1, f) == 1 && std::memcmp(h.magic, "SFCKPT2", 8) == 0 && h.paramsBytes == sizeof(sf_params) &&
+              std::fread(&p, sizeof(p), 1, f) == 1;
+    if(ok) { // every count is checked against the file size before anything is allocated from it
+        uint64_t need = sizeof(h) + sizeof(p) + static_cast<uint64_t>(h.n) * (h.hasIds ? 28u : 24u);
+        for(int w = 0; w < 6; ++w) need += static_cast<uint64_t>(h.wallCount[w]) * 12u;
+        ok = need == static_cast<uint64_t>(file_size(f)) && h.parts >= 1 && h.part == expectPart && h.part < h.parts &&
+             (h.hasIds ? h.nGlobal >= h.n && h.nGlobal <= 0xfffffff0ull : (h.parts == 1 && h.nGlobal == h.n));
+    }
+    std::vector<float> walls[6];
+    for(int w = 0; w < 6 && ok; ++w) {
+        walls[w].resize(static_cast<size_t>(h.wallCount[w]) * 3);
+        if(h.wallCount[w]) ok = std::fread(walls[w].data(), 12, h.wallCount[w], f) == h.wallCount[w];
+    }
+    if(ok && expectPart == 0) {
+        d.p        = p;
+        d.hasWalls = h.hasWalls != 0;
+        d.simTime  = h.simTime;
+        d.nGlobal  = h.nGlobal;
+        for(int w = 0; w < 6; ++w) d.walls[w] = walls[w];
+        d.x.assign(static_cast<size_t>(h.nGlobal) * 3, 0.f);
+        d.v.assign(static_cast<size_t>(h.nGlobal) * 3, 0.f);
+        if(seen) seen->assign(static_cast<size_t>(h.nGlobal), 0);
+    }
+    if(ok) ok = h.nGlobal == d.nGlobal && std::memcmp(&p, &d.p, sizeof(p)) == 0 && h.simTime == d.simTime;
+    if(ok && h.n) {
+        if(!h.hasIds) {
+            ok = std::fread(d.x.data(), 12, h.n, f) == h.n && std::fread(d.v.data(), 12, h.n, f) == h.n;
+            if(seen) std::fill(seen->begin(), seen->end(), 1);
+        } else {
+            std::vector<float>    x(static_cast<size_t>(h.n) * 3), v(static_cast<size_t>(h.n) * 3);
+            std::vector<uint32_t> id(h.n);
+            ok = std::fread(x.data(), 12, h.n, f) == h.n && std::fread(v.data(), 12, h.n, f) == h.n && std::fread(id.data(), 4, h.n, f) == h.n;
+            for(uint32_t i = 0; i < h.n && ok; ++i) {
+                ok = id[i] < d.nGlobal && !(*seen)[id[i]]; // every global id exactly once over all parts
+                if(!ok) break;
+                (*seen)[id[i]] = 1;
+                std::memcpy(&d.x[3 * static_cast<size_t>(id[i])], &x[3 * static_cast<size_t>(i)], 12);
+                std::memcpy(&d.v[3 * static_cast<size_t>(id[i])], &v[3 * static_cast<size_t>(i)], 12);
+            }
+        }
+    }
+    std::fclose(f);
+    if(partsOut) *partsOut = h.parts;
+    return ok;
+}
+
+// single file `path`, or the parts `path.0 .. path.<parts-1>` of a slab checkpoint
+int checkpoint_load(const char* path, CheckpointData& d)
+{
+    try {
+        std::vector<unsigned char> seen;
+        uint32_t                   parts = 1;
+        FILE*                      probe = std::fopen(path, "rb");
+        if(probe) {
+            std::fclose(probe);
+            if(!checkpoint_read_file(path, d, 0, &parts, &seen) || parts != 1) return fail(nullptr, SF_ERR_INVALID, std::string("not a valid checkpoint: ") + path);
+            return SF_OK;
+        }
+        const std::string base(path);
+        if(!checkpoint_read_file(base + ".0", d, 0, &parts, &seen)) return fail(nullptr, SF_ERR_INVALID, std::string("not a valid checkpoint: ") + path + "[.0]");
+        for(uint32_t k = 1; k < parts; ++k)
+            if(!checkpoint_read_file(base + "." + std::to_string(k), d, k, nullptr, &seen))
+                return fail(nullptr, SF_ERR_INVALID, std::string("missing or inconsistent checkpoint part ") + std::to_string(k) + " of " + path);
+        for(unsigned char c : seen)
+            if(!c) return fail(nullptr, SF_ERR_INVALID, std::string("checkpoint parts do not cover every particle id: ") + path);
+        return SF_OK;
+    } catch(const std::exception& e) { // bad_alloc / length_error never cross the C boundary
+        return fail(nullptr, SF_ERR_OOM, std::string("sf_checkpoint_read: ") + e.what());
+    }
+}
 } // namespace
 
 int sf_checkpoint_write(sf_solver* s, const char* path, float sim_time)
 {
     if(!s || !path) return SF_ERR_INVALID;
     if(!s->uploaded) return fail(s, SF_ERR_INVALID, "no particles uploaded");
-    if(s->slab.on) return fail(s, SF_ERR_INVALID, "checkpointing a slab run: gather with sf_download_owned");
-    const uint32_t     n = s->n;
-    std::vector<float> x(static_cast<size_t>(n) * 3), v(static_cast<size_t>(n) * 3);
-    int                rc = sf_download_positions(s, x.data());
-    if(rc) return rc;
-    rc = sf_download_velocities(s, v.data());
-    if(rc) return rc;
-    CheckpointHeader h{};
-    std::memcpy(h.magic, "SFCKPT1", 8);
-    h.paramsBytes = sizeof(sf_params);
-    h.n           = n;
-    h.simTime     = sim_time;
-    for(int w = 0; w < 6; ++w) h.wallCount[w] = static_cast<uint32_t>(s->walls[w].size() / 3);
-    FILE* f = std::fopen(path, "wb");
-    if(!f) return fail(s, SF_ERR_INVALID, std::string("cannot open ") + path);
-    bool ok = std::fwrite(&h, sizeof(h), 1, f) == 1 && std::fwrite(&s->params, sizeof(sf_params), 1, f) == 1;
-    for(int w = 0; w < 6 && ok; ++w)
-        if(h.wallCount[w]) ok = std::fwrite(s->walls[w].data(), 12, h.wallCount[w], f) == h.wallCount[w];
-    if(ok && n) ok = std::fwrite(x.data(), 12, n, f) == n && std::fwrite(v.data(), 12, n, f) == n;
-    std::fclose(f);
-    return ok ? SF_OK : fail(s, SF_ERR_INVALID, std::string("short write to ") + path);
+    try {
+        const bool            slab = s->slab.on;
+        uint32_t              n    = s->n;
+        std::vector<float>    x, v;
+        std::vector<uint32_t> id;
+        int                   rc;
+        if(slab) {
+            if(!s->ready) return fail(s, SF_ERR_INVALID, "slab mode: sf_make_ready before sf_checkpoint_write");
+            rc = sf_download_owned(s, nullptr, nullptr, nullptr, 0, &n);
+            if(rc) return rc;
+            x.resize(static_cast<size_t>(n) * 3);
+            v.resize(static_cast<size_t>(n) * 3);
+            id.resize(n);
+            uint32_t n2 = 0;
+            rc = sf_download_owned(s, id.data(), x.data(), v.data(), n, &n2);
+            if(rc) return rc;
+            if(n2 != n) return fail(s, SF_ERR_STATE, "owned particle count changed during the checkpoint");
+        } else {
+            x.resize(static_cast<size_t>(n) * 3);
+            v.resize(static_cast<size_t>(n) * 3);
+            rc = sf_download_positions(s, x.data());
+            if(rc) return rc;
+            rc = sf_download_velocities(s, v.data());
+            if(rc) return rc;
+        }
+        CheckpointHeader h{};
+        std::memcpy(h.magic, "SFCKPT2", 8);
+        h.paramsBytes = sizeof(sf_params);
+        h.n           = n;
+        h.simTime     = sim_time;
+        h.hasWalls    = s->wallsSet ? 1u : 0u;
+        h.hasIds      = slab ? 1u : 0u;
+        h.part        = slab ? static_cast<uint32_t>(s->slab.rank) : 0u;
+        h.parts       = slab ? static_cast<uint32_t>(s->slab.nranks) : 1u;
+        h.nGlobal     = slab ? s->slab.nGlobal : n;
+        for(int w = 0; w < 6; ++w) h.wallCount[w] = s->wallsSet ? static_cast<uint32_t>(s->walls[w].size() / 3) : 0u;
+        const std::string file = slab ? std::string(path) + "." + std::to_string(s->slab.rank) : std::string(path);
+        FILE* f = std::fopen(file.c_str(), "wb");
+        if(!f) return fail(s, SF_ERR_INVALID, std::string("cannot open ") + file);
+        bool ok = std::fwrite(&h, sizeof(h), 1, f) == 1 && std::fwrite(&s->params, sizeof(sf_params), 1, f) == 1;
+        for(int w = 0; w < 6 && ok; ++w)
+            if(h.wallCount[w]) ok = std::fwrite(s->walls[w].data(), 12, h.wallCount[w], f) == h.wallCount[w];
+        if(ok && n) ok = std::fwrite(x.data(), 12, n, f) == n && std::fwrite(v.data(), 12, n, f) == n;
+        if(ok && n && slab) ok = std::fwrite(id.data(), 4, n, f) == n;
+        ok = (std::fclose(f) == 0) && ok;
+        return ok ? SF_OK : fail(s, SF_ERR_INVALID, std::string("short write to ") + file);
+    } catch(const std::exception& e) {
+        return fail(s, SF_ERR_OOM, std::string("sf_checkpoint_write: ") + e.what());
+    }
 }
 
-int sf_checkpoint_read(const char* path, int device, sf_solver** out, float* sim_time)
+static int checkpoint_restore(const char* path, int device, int rank, int nranks, const void* id128, sf_solver** out, float* sim_time)
 {
     if(!path || !out) return fail(nullptr, SF_ERR_INVALID, "null argument");
-    *out    = nullptr;
-    FILE* f = std::fopen(path, "rb");
-    if(!f) return fail(nullptr, SF_ERR_INVALID, std::string("cannot open ") + path);
-    CheckpointHeader h{};
-    sf_params        p{};
-    bool ok = std::fread(&h, sizeof(h), 1, f) == 1 && std::memcmp(h.magic, "SFCKPT1", 8) == 0 && h.paramsBytes == sizeof(sf_params) &&
-              std::fread(&p, sizeof(p), 1, f) == 1;
-    std::vector<float> walls[6], x, v;
-    for(int w = 0; w < 6 && ok; ++w) {
-        walls[w].resize(static_cast<size_t>(h.wallCount[w]) * 3);
-        if(h.wallCount[w]) ok = std::fread(walls[w].data(), 12, h.wallCount[w], f) == h.wallCount[w];
-    }
-    if(ok) {
-        x.resize(static_cast<size_t>(h.n) * 3);
-        v.resize(static_cast<size_t>(h.n) * 3);
-        if(h.n) ok = std::fread(x.data(), 12, h.n, f) == h.n && std::fread(v.data(), 12, h.n, f) == h.n;
-    }
-    std::fclose(f);
-    if(!ok) return fail(nullptr, SF_ERR_INVALID, std::string("not a valid checkpoint: ") + path);
-    sf_solver* s  = nullptr;
-    int        rc = sf_create(&p, device, &s);
+    *out = nullptr;
+    CheckpointData d;
+    int            rc = checkpoint_load(path, d);
     if(rc) return rc;
-    for(int w = 0; w < 6 && !rc; ++w) rc = sf_set_boundary_particles(s, w, walls[w].data(), h.wallCount[w]);
-    if(!rc) rc = sf_upload_particles(s, x.data(), v.data(), h.n);
+    sf_solver* s = nullptr;
+    rc           = sf_create(&d.p, device, &s);
+    if(rc) return rc;
+    if(nranks > 1) rc = sf_comm_init(s, rank, nranks, id128);
+    // a checkpoint written before the walls existed restores none: sf_make_ready then generates the default ones
+    for(int w = 0; w < 6 && !rc && d.hasWalls; ++w) rc = sf_set_boundary_particles(s, w, d.walls[w].data(), static_cast<uint32_t>(d.walls[w].size() / 3));
+    if(!rc) rc = sf_upload_particles_global(s, d.x.data(), d.v.data(), static_cast<uint32_t>(d.nGlobal));
     if(!rc) rc = sf_make_ready(s);
     if(rc) {
         g_createError = s->lastError;
         sf_destroy(s);
         return rc;
     }
-    if(sim_time) *sim_time = h.simTime;
+    if(sim_time) *sim_time = d.simTime;
     *out = s;
     return SF_OK;
+}
+
+int sf_checkpoint_read(const char* path, int device, sf_solver** out, float* sim_time)
+{
+    return checkpoint_restore(path, device, 0, 1, nullptr, out, sim_time);
+}
+
+int sf_checkpoint_read_slab(const char* path, int device, int rank, int nranks, const void* id128, sf_solver** out, float* sim_time)
+{
+    if(nranks < 1 || rank < 0 || rank >= nranks || (nranks > 1 && !id128)) return fail(nullptr, SF_ERR_INVALID, "bad rank / nranks / id");
+    return checkpoint_restore(path, device, rank, nranks, id128, out, sim_time);
 }
 
 // ---- multi-GPU: z-slab decomposition (design notes in sf_slab.cuh) -----------------------------
@@ -1625,6 +1801,8 @@ int sf_comm_init(sf_solver* s, int rank, int nranks, const void* id128)
     SF_CUDA(s, cudaStreamCreateWithPriority(&L.commStream, cudaStreamNonBlocking, hi));
     SF_CUDA(s, cudaEventCreateWithFlags(&L.evEdge, cudaEventDisableTiming));
     SF_CUDA(s, cudaEventCreateWithFlags(&L.evExchanged, cudaEventDisableTiming));
+    SF_CUDA(s, cudaEventCreateWithFlags(&L.evInterior, cudaEventDisableTiming));
+    SF_CUDA(s, cudaEventCreateWithFlags(&L.evDt, cudaEventDisableTiming));
     SF_CUDA(s, dev_alloc(L.counters, 2));
     SF_CUDA(s, dev_alloc(L.row, kRowWords));
     SF_CUDA(s, dev_alloc(L.table, static_cast<size_t>(kRowWords) * nranks));
@@ -1632,9 +1810,19 @@ int sf_comm_init(sf_solver* s, int rank, int nranks, const void* id128)
     return SF_OK;
 }
 
+static int upload_particles_global(sf_solver* s, const float* pos_xyz, const float* vel_xyz, uint32_t n_global);
 int sf_upload_particles_global(sf_solver* s, const float* pos_xyz, const float* vel_xyz, uint32_t n_global)
 {
     if(!s || (!pos_xyz && n_global)) return SF_ERR_INVALID;
+    try {
+        return upload_particles_global(s, pos_xyz, vel_xyz, n_global);
+    } catch(const std::exception& e) { // host vectors of the scatter: nothing throws across the C boundary
+        return fail(s, SF_ERR_OOM, std::string("sf_upload_particles_global: ") + e.what());
+    }
+}
+
+static int upload_particles_global(sf_solver* s, const float* pos_xyz, const float* vel_xyz, uint32_t n_global)
+{
     if(!s->slab.on) return sf_upload_particles(s, pos_xyz, vel_xyz, n_global);
     SF_CUDA(s, cudaSetDevice(s->device));
     sf_solver::Slab& L = s->slab;
@@ -1664,17 +1852,19 @@ int sf_upload_particles_global(sf_solver* s, const float* pos_xyz, const float* 
     slab_plan(hist.data(), s->nS(), L.nranks, kMinThick, L.cur.data());
     L.next = L.cur;
     const int zb = L.cur[L.rank], ze = L.cur[L.rank + 1];
-    std::vector<float>    hp, hv;
-    std::vector<uint32_t> hid;
-    uint32_t              nOwn = 0;
+    uint64_t inWindow = 0; // particles of [zb - 3, ze + 3): from the layer histogram
+    for(int l = std::max(zb - kGhost, 0); l < std::min(ze + kGhost, s->nS()); ++l) inWindow += hist[l];
+    if(inWindow > 0xfffffff0ull) return fail(s, SF_ERR_OOM, "more than 2^32 particles on one rank");
+    std::vector<float>    hp(3 * inWindow), hv(vel_xyz ? 3 * inWindow : 0);
+    std::vector<uint32_t> hid(inWindow);
+    uint32_t              nOwn = 0, n = 0;
     for(uint32_t i = 0; i < n_global; ++i) {
         if(layer[i] < zb - kGhost || layer[i] >= ze + kGhost) continue;
-        hp.insert(hp.end(), pos_xyz + 3 * static_cast<size_t>(i), pos_xyz + 3 * static_cast<size_t>(i) + 3);
-        if(vel_xyz) hv.insert(hv.end(), vel_xyz + 3 * static_cast<size_t>(i), vel_xyz + 3 * static_cast<size_t>(i) + 3);
-        hid.push_back(i);
+        std::memcpy(&hp[3 * static_cast<size_t>(n)], pos_xyz + 3 * static_cast<size_t>(i), 12);
+        if(vel_xyz) std::memcpy(&hv[3 * static_cast<size_t>(n)], vel_xyz + 3 * static_cast<size_t>(i), 12);
+        hid[n++] = i;
         nOwn += (layer[i] >= zb && layer[i] < ze) ? 1u : 0u;
     }
-    const uint32_t n = static_cast<uint32_t>(hid.size());
     // room for load-balance drift, ghosts and the dead slots of one substep
     // SF_SLAB_TIGHT (tests): start with almost no headroom so that the on-demand growth paths are exercised
     const bool     tight = std::getenv("SF_SLAB_TIGHT") != nullptr;
@@ -1722,37 +1912,132 @@ int sf_slab_info(sf_solver* s, int32_t* z_begin, int32_t* z_end, uint32_t* n_own
     return SF_OK;
 }
 
+namespace
+{
+int owned_scratch(sf_solver* s)
+{
+    if(!s->ownCounters) {
+        SF_CUDA(s, cudaMalloc(reinterpret_cast<void**>(&s->ownCounters), 4 * sizeof(uint32_t)));
+        SF_CUDA(s, cudaMallocHost(reinterpret_cast<void**>(&s->hostOwnCounters), 4 * sizeof(uint32_t)));
+    }
+    return SF_OK;
+}
+
+// own layer range of this rank by the CURRENT cut planes (global layers along the slow axis)
+void owned_range(const sf_solver* s, int& zb, int& ze)
+{
+    zb = s->slab.on ? s->slab.cur[s->slab.rank] : 0;
+    ze = s->slab.on ? s->slab.cur[s->slab.rank + 1] : s->nS();
+}
+
+// Compacts the owned particles on the device (k_owned_gather) into the xyz staging arrays + B.keys[0] (free between
+// substeps) and copies the first min(count, cap) to the host buffers that are given.  *n_out = owned count.
+int gather_owned(sf_solver* s, uint32_t* ids, float* pos_xyz, float* vel_xyz, uint32_t cap, uint32_t* n_out)
+{
+    int rc = owned_scratch(s);
+    if(rc) return rc;
+    const uint32_t m = s->slab.on ? s->nSlots : s->n;
+    int            zb, ze;
+    owned_range(s, zb, ze);
+    cudaStream_t st   = s->stream;
+    float*       dpos = s->stage;
+    float*       dvel = s->stage + 3 * static_cast<size_t>(s->npad);
+    SF_CUDA(s, cudaMemsetAsync(s->ownCounters, 0, 4 * sizeof(uint32_t), st));
+    if(m) {
+        LaunchScope ls(s, K_MARSHAL);
+        k_owned_gather<<<std::min<uint32_t>(cdiv(m, 256), s->numSMs * 16), 256, 0, st>>>(s->B.posA, s->B.velA, s->B.idA, m, s->P, zb, ze, dpos, dvel,
+                                                                                           s->B.keys[0], s->npad, s->ownCounters);
+    }
+    SF_CUDA(s, cudaMemcpyAsync(s->hostOwnCounters, s->ownCounters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    SF_CUDA(s, cudaStreamSynchronize(st));
+    const uint32_t k = s->hostOwnCounters[2];
+    *n_out           = k;
+    const uint32_t c = std::min(k, cap);
+    if(c && (ids || pos_xyz || vel_xyz)) {
+        if(pos_xyz) SF_CUDA(s, cudaMemcpyAsync(pos_xyz, dpos, static_cast<size_t>(c) * 12, cudaMemcpyDeviceToHost, st));
+        if(vel_xyz) SF_CUDA(s, cudaMemcpyAsync(vel_xyz, dvel, static_cast<size_t>(c) * 12, cudaMemcpyDeviceToHost, st));
+        if(ids) SF_CUDA(s, cudaMemcpyAsync(ids, s->B.keys[0], static_cast<size_t>(c) * 4, cudaMemcpyDeviceToHost, st));
+        SF_CUDA(s, cudaStreamSynchronize(st));
+    }
+    return SF_OK;
+}
+} // namespace
+
 int sf_download_owned(sf_solver* s, uint32_t* ids, float* pos_xyz, float* vel_xyz, uint32_t cap, uint32_t* n_out)
 {
     if(!s || !n_out) return SF_ERR_INVALID;
     if(!s->uploaded) return fail(s, SF_ERR_INVALID, "no particles uploaded");
+    if(!s->ready) return fail(s, SF_ERR_INVALID, "sf_make_ready has not been called");
     SF_CUDA(s, cudaSetDevice(s->device));
-    SF_CUDA(s, cudaStreamSynchronize(s->stream));
-    const uint32_t      m = s->slab.on ? s->nSlots : s->n;
-    std::vector<float4> hx(m), hv(m);
-    std::vector<uint32_t> hid(m);
-    if(m) {
-        SF_CUDA(s, cudaMemcpy(hx.data(), s->B.posA, sizeof(float4) * m, cudaMemcpyDeviceToHost));
-        SF_CUDA(s, cudaMemcpy(hv.data(), s->B.velA, sizeof(float4) * m, cudaMemcpyDeviceToHost));
-        SF_CUDA(s, cudaMemcpy(hid.data(), s->B.idA, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost));
-    }
-    int32_t g[3];
-    grid_dims(s->params, g);
-    const int zb = s->slab.on ? s->slab.cur[s->slab.rank] : 0, ze = s->slab.on ? s->slab.cur[s->slab.rank + 1] : g[s->axisS];
-    uint32_t  k = 0;
-    for(uint32_t i = 0; i < m; ++i) {
-        if(hid[i] == kInvalidId) continue;
-        const int32_t lz = cell_layer(s->params, g[s->axisS], s->axisS == 1 ? hx[i].y : hx[i].z, s->axisS);
-        if(lz < zb || lz >= ze) continue;
-        if(k < cap) {
-            if(ids) ids[k] = hid[i];
-            if(pos_xyz) { pos_xyz[3 * k] = hx[i].x; pos_xyz[3 * k + 1] = hx[i].y; pos_xyz[3 * k + 2] = hx[i].z; }
-            if(vel_xyz) { vel_xyz[3 * k] = hv[i].x; vel_xyz[3 * k + 1] = hv[i].y; vel_xyz[3 * k + 2] = hv[i].z; }
-        }
-        ++k;
-    }
-    *n_out = k;
+    return gather_owned(s, ids, pos_xyz, vel_xyz, cap, n_out);
+}
+
+int sf_slab_axis(sf_solver* s, int32_t* axis_out)
+{
+    if(!s || !axis_out) return SF_ERR_INVALID;
+    *axis_out = s->axisS;
     return SF_OK;
+}
+
+// Host-owned slab step: the multi-GPU counterpart of sf_step_host.  Between two calls the host holds this rank's
+// OWNED particles {id, position, velocity} (28 B each); the ghost particles of the coming substep stay resident on
+// the device -- they arrived with the previous exchange and belong to the neighbours.  One call = upload the m_in
+// owned particles (the resident copies are dropped), one substep incl. the halo exchange and migration, download
+// the particles this rank owns afterwards (*m_out of them, any order; at most cap are written).
+int sf_step_host_owned(sf_solver* s, uint32_t* ids, float* pos_xyz, float* vel_xyz, uint32_t m_in, uint32_t cap, uint32_t* m_out, float* dt_out)
+{
+    int rc = require_ready(s);
+    if(rc) return rc;
+    if(!ids || !pos_xyz || !vel_xyz || !m_out) return SF_ERR_INVALID;
+    if(!s->slab.on) return fail(s, SF_ERR_INVALID, "sf_step_host_owned is the slab-mode call: use sf_step_host on a single GPU");
+    SF_CUDA(s, cudaSetDevice(s->device));
+    rc = owned_scratch(s);
+    if(rc) return rc;
+    cudaStream_t st = s->stream;
+    SF_CUDA(s, cudaStreamSynchronize(st));
+    SF_CUDA(s, cudaStreamSynchronize(s->slab.commStream)); // the in-flight all-reduce writes the max |v|^2 slots reset below
+    if(static_cast<uint64_t>(s->nSlots) + m_in > s->cap) {
+        const uint64_t want = static_cast<uint64_t>(s->nSlots) + m_in;
+        if(want + want / 4 > 0xfffffff0ull) return fail(s, SF_ERR_OOM, "more than 2^32 particle slots on one rank");
+        SF_CUDA(s, cudaStreamSynchronize(s->slab.commStream));
+        rc = ensure_particle_capacity(s, static_cast<uint32_t>(want + want / 4), s->nSlots);
+        if(rc) return rc;
+        s->slab.regrowths++;
+    }
+    int zb, ze;
+    owned_range(s, zb, ze);
+    float*    dpos = s->stage;
+    float*    dvel = s->stage + 3 * static_cast<size_t>(s->npad);
+    uint32_t* dids = s->B.vals[0]; // free between substeps
+    if(m_in) {
+        SF_CUDA(s, cudaMemcpyAsync(dpos, pos_xyz, static_cast<size_t>(m_in) * 12, cudaMemcpyHostToDevice, st));
+        SF_CUDA(s, cudaMemcpyAsync(dvel, vel_xyz, static_cast<size_t>(m_in) * 12, cudaMemcpyHostToDevice, st));
+        SF_CUDA(s, cudaMemcpyAsync(dids, ids, static_cast<size_t>(m_in) * 4, cudaMemcpyHostToDevice, st));
+    }
+    SF_CUDA(s, cudaMemsetAsync(s->ownCounters, 0, 4 * sizeof(uint32_t), st));
+    {
+        LaunchScope ls(s, K_MARSHAL);
+        // computeMaxVel (A.5) restarts from the uploaded velocities: this rank's slot goes back to FLT_MIN first
+        k_owned_reset_maxvel<<<1, 1, 0, st>>>(s->B.state);
+        if(s->nSlots) k_owned_kill<<<std::min<uint32_t>(cdiv(s->nSlots, 256), s->numSMs * 16), 256, 0, st>>>(s->B.posA, s->B.idA, s->nSlots, s->P, zb, ze, s->ownCounters);
+        if(m_in) k_owned_append<<<std::min<uint32_t>(cdiv(m_in, 256), s->numSMs * 16), 256, 0, st>>>(dpos, dvel, dids, m_in, s->B.posA + s->nSlots, s->B.velA + s->nSlots,
+                                                                                                     s->B.idA + s->nSlots, s->P, zb, ze, s->ownCounters, s->B.state);
+    }
+    SF_CUDA(s, cudaMemcpyAsync(s->hostOwnCounters, s->ownCounters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    SF_CUDA(s, cudaStreamSynchronize(st));
+    if(s->hostOwnCounters[1])
+        return fail(s, SF_ERR_DOMAIN, std::to_string(s->hostOwnCounters[1]) + " uploaded particles lie outside the box or outside this rank's cell layers");
+    const uint32_t killed = s->hostOwnCounters[0];
+    s->n      = s->n - std::min(s->n, killed) + m_in;
+    s->nSlots = s->nSlots + m_in;
+    s->P.n    = s->n;
+    s->slab.dtReduced = false; // max |v|^2 changed: all-reduce in-stream before the force pass
+    rc = enqueue_substep(s);
+    if(rc) return rc;
+    rc = read_state(s);
+    if(rc) return rc;
+    if(dt_out) *dt_out = s->hostState->dt;
+    return gather_owned(s, ids, pos_xyz, vel_xyz, cap, m_out);
 }
 
 // raw local state (live + dead slots) <-> host: what bench.py's multi-GPU e2e leg moves every substep

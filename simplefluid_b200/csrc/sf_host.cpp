@@ -278,11 +278,19 @@ void slab_rebalance(const uint32_t* table, int32_t rowWords, int32_t nranks, int
 // ------------------------------------------------------------------------------------------------
 // Wall patches (A.4): 6 walls x (nA x nA x nB) jittered points hanging outside the box; the patch
 // is expressed in wall-local tangential coordinates and follows the particle (A.6).
+// Per wall the binary draws three numbers (EXE@0x14001705a-0x1400172e0) and gives them these roles -- J = tangential
+// jitter d*(hi-lo)+lo, D = depth jitter d*(lo-0)+0, ti / tj = lattice coordinate of the outer / middle loop:
+//   LX, UX: x = normal + D(d3)   y = J(d2) + ti       z = J(d1) + tj
+//   LY, UY: x = J(d3) + ti       y = normal + D(d2)   z = J(d1) + tj
+//   LZ, UZ: x = J(d3) + ti       y = J(d2) + tj       z = normal + D(d1)
+// with normal = boxMin - depth (lower walls) or depth + boxMax (upper walls).  tests/test_oracle_vs_exe.py checks this
+// table against the disassembly.
 void generate_boundary(const sf_params& p, uint32_t seed, std::vector<float> walls[6])
 {
     std::mt19937 gen(seed);
-    // generate_canonical<float, 24>: one 32-bit draw, top 24 bits -> [0, 1)
-    auto U = [&gen]() { return static_cast<float>(gen() >> 8) * (1.0f / 16777216.0f); };
+    // MSVC's std::generate_canonical<float, 24> over mt19937 (EXE@0x1400101a0): one 32-bit draw converted to float
+    // (round to nearest) and divided by 2^32f -- so it can return exactly 1.0f, as in the reference binary
+    auto U = [&gen]() { return static_cast<float>(static_cast<uint32_t>(gen())) / 4294967296.0f; };
 
     const float r = p.particleRadius, h = p.kernelRadius;
     const float jitLo = static_cast<float>(static_cast<double>(r) * 0.1);
@@ -295,6 +303,9 @@ void generate_boundary(const sf_params& p, uint32_t seed, std::vector<float> wal
         walls[w].clear();
         walls[w].reserve(static_cast<size_t>(nA) * nA * nB * 3);
     }
+    // role of draw 1 / 2 / 3 per axis of the wall normal: 0 = normal (depth jitter), 1 = x, 2 = y, 3 = z tangential
+    auto J = [&](float d) { return d * (jitHi - jitLo) + jitLo; };
+    auto D = [&](float d) { return d * (jitLo - 0.0f) + 0.0f; };
     for(int i = 0; i < nA; ++i) {
         for(int j = 0; j < nA; ++j) {
             for(int k = 0; k < nB; ++k) {
@@ -302,16 +313,22 @@ void generate_boundary(const sf_params& p, uint32_t seed, std::vector<float> wal
                 const float tj    = base + static_cast<float>(j) * pitch;
                 const float depth = static_cast<float>(k) * pitch + r;
                 for(int w = 0; w < 6; ++w) { // LX UX LY UY LZ UZ, three fresh draws each
-                    const float a    = U() * (jitHi - jitLo) + jitLo;
-                    const float b    = U() * (jitHi - jitLo) + jitLo;
-                    const float c    = U() * (jitLo - 0.0f) + 0.0f;
+                    const float d1 = U(), d2 = U(), d3 = U();
                     const int   axis = w / 2;
-                    const float nrm  = (w & 1) ? (p.boxMax[axis] + depth) + c : (p.boxMin[axis] - depth) + c;
+                    const float nrm  = (w & 1) ? depth + p.boxMax[axis] : p.boxMin[axis] - depth;
                     float       q[3];
-                    int         t = 0;
-                    for(int d = 0; d < 3; ++d) {
-                        if(d == axis) q[d] = nrm;
-                        else q[d] = (t++ == 0) ? ti + b : tj + a;
+                    if(axis == 0) {
+                        q[2] = J(d1) + tj;
+                        q[1] = J(d2) + ti;
+                        q[0] = nrm + D(d3);
+                    } else if(axis == 1) {
+                        q[2] = J(d1) + tj;
+                        q[1] = nrm + D(d2);
+                        q[0] = J(d3) + ti;
+                    } else {
+                        q[2] = nrm + D(d1);
+                        q[1] = J(d2) + tj;
+                        q[0] = J(d3) + ti;
                     }
                     walls[w].insert(walls[w].end(), q, q + 3);
                 }

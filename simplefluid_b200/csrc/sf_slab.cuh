@@ -149,6 +149,108 @@ __global__ void k_slab_unpack(const float4* __restrict__ recv, uint32_t count, f
     id[i]  = __float_as_uint(a.w);
 }
 
+// ---- host-owned slab state (sf_step_host_owned / sf_download_owned): every rank's OWNED particles live on the host
+// between substeps; the ghost particles of the next substep stay resident (they came with the last exchange).
+// counters: [0] = resident owned particles dropped, [1] = uploaded particles outside the box or this rank's layers,
+// [2] = owned particles gathered.
+__device__ __forceinline__ bool slab_in_box(const DevParams& P, float x, float y, float z)
+{
+    const float c[3] = { x, y, z };
+    const int   g[3] = { P.nx, P.axisS == 1 ? P.nzGlobal : P.ny, P.axisS == 2 ? P.nzGlobal : P.ny };
+    for(int d = 0; d < 3; ++d) { // the host's cell_coords_checked (sf_host.cpp), same float ops
+        const float t = (c[d] - P.bmin[d]) / P.h;
+        if(!(t >= 0.0f) || !(t < static_cast<float>(g[d]))) return false; // also rejects NaN / inf
+    }
+    return true;
+}
+
+__global__ void k_owned_reset_maxvel(DevState* st) { st->maxv2Bits[st->step & 1u] = __float_as_uint(FLT_MIN); }
+
+// the resident copies of this rank's own particles give way to the host's
+__global__ void k_owned_kill(const float4* __restrict__ posA, uint32_t* __restrict__ idA, uint32_t nSlots, DevParams P, int zb, int ze,
+                             uint32_t* __restrict__ counters)
+{
+    uint32_t killed = 0u;
+    for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nSlots; i += gridDim.x * blockDim.x) {
+        if(idA[i] == kInvalidId) continue;
+        const int cz = cell_layer_global(P, posA[i]);
+        if(cz >= zb && cz < ze) {
+            idA[i] = kInvalidId;
+            ++killed;
+        }
+    }
+    for(int o = 16; o > 0; o >>= 1) killed += __shfl_xor_sync(0xffffffffu, killed, o);
+    if((threadIdx.x & 31) == 0 && killed) atomicAdd(&counters[0], killed);
+}
+
+// the host's owned set appended behind the resident slots, with computeMaxVel (A.5) of the uploaded velocities
+__global__ void k_owned_append(const float* __restrict__ posXYZ, const float* __restrict__ velXYZ, const uint32_t* __restrict__ ids, uint32_t m,
+                               float4* __restrict__ pos, float4* __restrict__ vel, uint32_t* __restrict__ id, DevParams P, int zb, int ze,
+                               uint32_t* __restrict__ counters, DevState* st)
+{
+    float    mx  = FLT_MIN;
+    uint32_t bad = 0u;
+    for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+        const float4 x = make_float4(posXYZ[3 * static_cast<size_t>(i)], posXYZ[3 * static_cast<size_t>(i) + 1], posXYZ[3 * static_cast<size_t>(i) + 2], 0.f);
+        const float4 v = make_float4(velXYZ[3 * static_cast<size_t>(i)], velXYZ[3 * static_cast<size_t>(i) + 1], velXYZ[3 * static_cast<size_t>(i) + 2], 0.f);
+        const int    cz = cell_layer_global(P, x);
+        if(!slab_in_box(P, x.x, x.y, x.z) || cz < zb || cz >= ze) ++bad;
+        pos[i] = x;
+        vel[i] = v;
+        id[i]  = ids[i];
+        mx     = fmaxf(mx, (v.y * v.y + v.x * v.x) + v.z * v.z);
+    }
+    for(int o = 16; o > 0; o >>= 1) {
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        bad += __shfl_xor_sync(0xffffffffu, bad, o);
+    }
+    if((threadIdx.x & 31) == 0) {
+        if(mx > FLT_MIN) atomicMax(&st->maxv2Bits[st->step & 1u], __float_as_uint(mx));
+        if(bad) atomicAdd(&counters[1], bad);
+    }
+}
+
+// compaction of the particles this rank owns ([zb, ze) by the CURRENT cut planes) into xyz staging arrays; the
+// order is whatever the atomics give (the ids travel with the particles)
+__global__ void k_owned_gather(const float4* __restrict__ posA, const float4* __restrict__ velA, const uint32_t* __restrict__ idA, uint32_t nSlots,
+                               DevParams P, int zb, int ze, float* __restrict__ posXYZ, float* __restrict__ velXYZ, uint32_t* __restrict__ ids,
+                               uint32_t cap, uint32_t* __restrict__ counters)
+{
+    const int lane = threadIdx.x & 31;
+    for(uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < nSlots; base += gridDim.x * blockDim.x) {
+        const uint32_t i = base + lane;
+        bool           own = false;
+        float4         x = make_float4(0.f, 0.f, 0.f, 0.f);
+        uint32_t       pid = kInvalidId;
+        if(i < nSlots) {
+            pid = idA[i];
+            if(pid != kInvalidId) {
+                x            = posA[i];
+                const int cz = cell_layer_global(P, x);
+                own          = cz >= zb && cz < ze;
+            }
+        }
+        const uint32_t mask = __ballot_sync(0xffffffffu, own);
+        if(!mask) continue;
+        uint32_t k0 = 0u;
+        if(lane == 0) k0 = atomicAdd(&counters[2], static_cast<uint32_t>(__popc(mask)));
+        k0 = __shfl_sync(0xffffffffu, k0, 0);
+        if(own) {
+            const uint32_t k = k0 + __popc(mask & ((1u << lane) - 1u));
+            if(k < cap) {
+                const float4 v = velA[i];
+                posXYZ[3 * static_cast<size_t>(k)]     = x.x;
+                posXYZ[3 * static_cast<size_t>(k) + 1] = x.y;
+                posXYZ[3 * static_cast<size_t>(k) + 2] = x.z;
+                velXYZ[3 * static_cast<size_t>(k)]     = v.x;
+                velXYZ[3 * static_cast<size_t>(k) + 1] = v.y;
+                velXYZ[3 * static_cast<size_t>(k) + 2] = v.z;
+                ids[k] = pid;
+            }
+        }
+    }
+}
+
 __global__ void k_pack_upload_ids(const float* __restrict__ posXYZ, const float* __restrict__ velXYZ, const uint32_t* __restrict__ ids,
                                   float4* __restrict__ pos, float4* __restrict__ vel, uint32_t* __restrict__ id, uint32_t n)
 {

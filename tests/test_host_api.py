@@ -161,3 +161,71 @@ def test_cpp_facade_headers_compile():
         assert r.returncode == 0, r.stderr
         # scene generation is host-side: runs without a GPU and reproduces the reference's CubeDrop count (Captured/2.png)
         assert subprocess.run([exe]).returncode == 0
+
+
+# ---- checkpoint files: every count is validated against the file size before anything is allocated ------------
+def _checkpoint_bytes(sf, n=5, walls=(2, 0, 0, 0, 0, 1), part=0, parts=1, n_global=None, ids=None, magic=b"SFCKPT2\0"):
+    import struct
+    p = sf.default_params(24, "Dambreak")
+    has_ids = ids is not None
+    n_global = n if n_global is None else n_global
+    hdr = struct.pack("<8sII6IfIIII4xQ", magic, C.sizeof(p), n, *walls, 0.25, 1, 1 if has_ids else 0, part, parts, n_global)
+    assert len(hdr) == 72
+    body = bytes(p)
+    for w in walls:
+        body += np.zeros((w, 3), np.float32).tobytes()
+    x = np.linspace(-0.5, 0.5, 3 * n, dtype=np.float32).reshape(n, 3)
+    body += x.tobytes() + np.zeros((n, 3), np.float32).tobytes()
+    if has_ids:
+        body += np.asarray(ids, np.uint32).tobytes()
+    return hdr + body
+
+
+def _read_checkpoint(sf, path):
+    L = sf.library()
+    h, t = C.c_void_p(), C.c_float(0)
+    rc = L.sf_checkpoint_read(str(path).encode(), 0, C.byref(h), C.byref(t))
+    msg = (L.sf_last_error(None) or b"").decode()
+    if rc == 0:
+        L.sf_destroy(h)
+    return rc, msg
+
+
+def test_checkpoint_files_are_validated_before_use(sf, tmp_path):
+    import struct
+    good = _checkpoint_bytes(sf)
+    f = tmp_path / "good.ckpt"
+    f.write_bytes(good)
+    rc, msg = _read_checkpoint(sf, f)
+    # without a GPU a VALID file gets as far as sf_create (no CPU fallback); with one it restores
+    assert rc in (0, -2), (rc, msg)
+    cases = {
+        "truncated": good[:-7],
+        "trailing": good + b"\0" * 4,
+        "bad magic": _checkpoint_bytes(sf, magic=b"SFCKPT1\0"),
+        "huge n": good[:12] + struct.pack("<I", 0xFFFFFFF0) + good[16:],
+        "huge wall count": good[:16] + struct.pack("<I", 0x7FFFFFFF) + good[20:],
+        "part of a slab checkpoint as a whole file": _checkpoint_bytes(sf, n=2, parts=2, n_global=4, ids=[0, 1]),
+        "header only": good[:72],
+        "empty": b"",
+    }
+    for name, data in cases.items():
+        g = tmp_path / "bad.ckpt"
+        g.write_bytes(data)
+        rc, msg = _read_checkpoint(sf, g)
+        assert rc == -1, (name, rc, msg)
+    assert _read_checkpoint(sf, tmp_path / "missing.ckpt")[0] == -1
+
+
+def test_slab_checkpoint_parts_must_partition_the_ids(sf, tmp_path):
+    base = tmp_path / "run.ckpt"
+    (tmp_path / "run.ckpt.0").write_bytes(_checkpoint_bytes(sf, n=3, part=0, parts=2, n_global=5, ids=[0, 2, 4]))
+    (tmp_path / "run.ckpt.1").write_bytes(_checkpoint_bytes(sf, n=2, part=1, parts=2, n_global=5, ids=[1, 3]))
+    rc, msg = _read_checkpoint(sf, base)
+    assert rc in (0, -2), (rc, msg)  # consistent parts: parsed, then sf_create (GPU) or SF_ERR_CUDA (none)
+    (tmp_path / "run.ckpt.1").write_bytes(_checkpoint_bytes(sf, n=2, part=1, parts=2, n_global=5, ids=[1, 2]))  # id 2 twice, 3 missing
+    assert _read_checkpoint(sf, base)[0] == -1
+    (tmp_path / "run.ckpt.1").write_bytes(_checkpoint_bytes(sf, n=2, part=1, parts=2, n_global=5, ids=[1, 9]))  # id out of range
+    assert _read_checkpoint(sf, base)[0] == -1
+    os.remove(tmp_path / "run.ckpt.1")
+    assert _read_checkpoint(sf, base)[0] == -1  # a part is missing

@@ -18,16 +18,19 @@ def _ngpu():
         return 0
 
 
-@pytest.mark.parametrize("world,scene,res,steps,env", [
-    (2, "Dambreak", 32, 300, {}),                                   # y-slabs (auto), migration, moving cut planes
-    (4, "DoubleDambreak", 48, 120, {}),                             # z-slabs (auto)
-    (2, "Dambreak", 40, 800, {"SF_SLAB_TIGHT": "1"}),               # no capacity headroom: on-demand growth paths
-    (2, "SphereDrop", 32, 200, {"SF_SLAB_AXIS": "y"}),              # forced axis
+@pytest.mark.parametrize("world,scene,res,steps,env,mode", [
+    (2, "Dambreak", 32, 300, {}, "resident"),                       # y-slabs (auto), migration, moving cut planes
+    (4, "DoubleDambreak", 48, 120, {}, "resident"),                 # z-slabs (auto)
+    (2, "Dambreak", 40, 800, {"SF_SLAB_TIGHT": "1"}, "resident"),   # no capacity headroom: on-demand growth paths
+    (2, "SphereDrop", 32, 200, {"SF_SLAB_AXIS": "y"}, "resident"),  # forced axis
+    (2, "Dambreak", 32, 200, {}, "host_owned"),                     # sf_step_host_owned: owned particles live on the host
+    (2, "Dambreak", 32, 200, {"SF_SLAB_TIGHT": "1"}, "host_owned"),
+    (2, "DoubleDambreak", 40, 160, {}, "checkpoint"),               # per-rank checkpoint parts, restored on 2 ranks and on 1
 ])
-def test_slabs_bit_identical_to_single_gpu(sf, world, scene, res, steps, env):
+def test_slabs_bit_identical_to_single_gpu(sf, world, scene, res, steps, env, mode):
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", str(29600 + world), os.path.join(ROOT, "tools", "mgpu_check.py"), scene, str(res), str(steps)]
+           "--master-port", str(29600 + world), os.path.join(ROOT, "tools", "mgpu_check.py"), scene, str(res), str(steps), mode]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env={**os.environ, **env})
     assert out.returncode == 0 and "MGPU OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]

@@ -521,7 +521,7 @@ def test_developed_flow_vs_oracle(sf, ob):
     x, v = g0.getParticles(), g0.getVelocity()
     d0 = g0.diagnostics()
     g0.close()
-    assert d0["nbr_mean"] > 33 and x[:, 2].max() > 0.9  # the flow has developed
+    assert d0["nbr_mean"] > 31 and x[:, 2].max() > 0.9  # the flow has developed (the rest lattice has < 28 neighbours on average)
     gpu, orc, _ = make_pair(sf, ob, "Dambreak", 64, pos=x, vel=v)
     inv_step = float(sf.binding.build_tables(p)[2][2])
     for _ in range(3):
