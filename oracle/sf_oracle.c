@@ -1,6 +1,6 @@
 /*
  * sf_oracle.c -- CPU oracle for the SimpleFluid SPH step.  TEST INFRASTRUCTURE ONLY
- * (see sf_oracle.h for scope, provenance and the "parity unpinned by the reference" note).
+ * (see sf_oracle.h for scope, provenance and how it is pinned to the reference binary's own outputs).
  *
  * Build: gcc -O2 -ffp-contract=off -fno-fast-math -fopenmp   (the MSVC reference binary uses
  * separately rounded SSE scalar ops, no FMA -- SURVEY.md section 0 item 5).

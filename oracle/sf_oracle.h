@@ -9,11 +9,16 @@
  * plus Source/SceneManager.cpp:41-173 (scenes), Source/Simulator.cpp:44-56 (substep loop) and
  * Source/Controller.cpp:52-64 (parameters).
  *
- * PARITY STATUS: the reference ships no tests, golden vectors or fixtures for this path, and
- * neither the source nor the Windows binary can be built/run here => "parity unpinned by the
- * reference".  What pins this oracle: (1) the scene generator is checked against the reference's
- * own Source/SceneManager.cpp compiled unmodified (oracle/_ref, see oracle/Makefile) and against
- * the particle counts in the reference's screenshots (Captured/1.png..3.png); (2) the analytic
+ * PARITY STATUS: PINNED against outputs of the reference itself.  The reference ships no tests or golden vectors and
+ * its solver source is absent, but its compiled solver is not: oracle/exe/sf_exe_harness.c maps the shipped binary
+ * Prebuild/SimpleFluid.exe and calls its own SPHSolver::makeReady (EXE@0x140016650) and SPHSolver::advanceFrame
+ * (EXE@0x140016810) natively (imports bound to libm / malloc / a single-threaded stand-in for the TBB scheduler).
+ * This oracle reproduces that code's results BIT FOR BIT -- kernel tables, wall particles (same seed), dt, cell
+ * indices, density, acceleration, positions, velocities; every scene, the Shepard / attractive-pressure / no-wall
+ * variants, an odd grid, random moving states, 1000 substeps of the reference default: tests/test_oracle_vs_exe.py
+ * (live runs in the build container + the committed fixtures tests/golden/exe_*.npz everywhere).  Also: (1) the scene
+ * generator is checked against the reference's own Source/SceneManager.cpp compiled unmodified (oracle/_ref, see
+ * oracle/Makefile) and the particle counts in the reference's screenshots (Captured/1.png..3.png); (2) the analytic
  * known answers of SURVEY.md section 8c (tests/test_oracle.py).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may

@@ -105,6 +105,35 @@ def test_config2_cube_drop_one_million(sf, ob):
     orc.close()
 
 
+@pytest.mark.parametrize("name", __import__("exe_golden").CASES)
+def test_cuda_path_reproduces_the_reference_binarys_outputs(sf, name):
+    """The CUDA path against OUTPUTS OF THE REFERENCE ITSELF: tests/golden/exe_*.npz were produced by the reference's own
+    compiled makeReady / advanceFrame (Prebuild/SimpleFluid.exe run natively, tests/golden/make_exe_golden.py).  Bit for bit:
+    kernel tables, wall particles, the dt sequence (1000 substeps of the reference default incl. CFL-limited ones), and
+    cell indices / density / acceleration / positions / velocities at the stored substeps -- no oracle in between."""
+    import exe_golden
+    g = exe_golden.load(name)
+    p = sf.default_params(g["resolution"], g["scene"], **g["overrides"])
+    pos = sf.scene_generate(p)
+    assert len(pos) == int(g["n"])
+    gpu = sf.SPHSolver(p)
+    gpu.setParticles(pos)
+    gpu.generateBoundaryParticles(g["seed"])
+    gpu.setCapture(True)
+    gpu.makeReady()
+    assert tuple(gpu.gridDims()) == tuple(int(x) for x in g["grid"])
+    assert np.float32(gpu.params.particleMass) == g["particleMass"] or np.float32(p.particleMass) == g["particleMass"]
+    if "cubic_W" in g:
+        assert exact(gpu.field(sf.binding.FIELD_TABLE_CUBIC_W)[:10000], g["cubic_W"])
+        assert exact(gpu.field(sf.binding.FIELD_TABLE_SPIKY_GRAD), g["spiky_gradW"])
+        for w in range(6):
+            assert exact(gpu.getBoundaryParticles(w), g[f"wall{w}"]), f"wall {w}"
+    n = exe_golden.replay(g, gpu.advanceFrame,
+                          lambda: dict(cell=gpu.cellIndex(), rho=gpu.density(), acc=gpu.accel(), x=gpu.getParticles(), v=gpu.getVelocity()))
+    assert n == len(g["dts"])
+    gpu.close()
+
+
 def test_1000_substeps_dambreak_reference_default(sf, ob):
     """Positions after 1000 substeps (~1 s: the whole collapse-and-splash phase).  Stated tolerance: 0
     (bit-identical); the looser 1e-5*box gate is asserted first to size any regression."""
