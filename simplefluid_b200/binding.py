@@ -9,7 +9,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
-_LIB_PATH = os.path.join(_HERE, "lib", "libsf_b200.so")
+_LIB_PATH = os.environ.get("SF_B200_LIB") or os.path.join(_HERE, "lib", "libsf_b200.so")  # SF_B200_LIB: kernel experiments (tools/exp_bench.py)
 
 SCENES = {"SphereDrop": 0, "CubeDrop": 1, "Dambreak": 2, "DoubleDambreak": 3}  # Include/Common.h:52-58
 

@@ -14,7 +14,10 @@ namespace sf
 {
 constexpr int kTab = 10000;
 // work unit of the pair kernels (sf_pairs.cuh): a brick of BX x BY x BZ grid cells
-constexpr int BX = 8, BY = 4, BZ = 4;
+#ifndef SF_BZ
+#define SF_BZ 4
+#endif
+constexpr int BX = 8, BY = 4, BZ = SF_BZ;
 
 // ------------------------------------------------------------------------------------------------
 // small helpers
