@@ -106,6 +106,7 @@ struct sf_solver {
         // only before the force pass of the next substep (dtReduced: evDt covers the current maxv2Bits)
         cudaEvent_t          evInterior = nullptr, evDt = nullptr;
         bool                 dtReduced = false;
+        int                  ghost = 3; // ghost layers per side this rank holds (fixed at sf_upload_particles_global)
     } slab;
     uint32_t *ownCounters = nullptr, *hostOwnCounters = nullptr; // device / pinned: sf_download_owned, sf_step_host_owned
 
@@ -251,8 +252,8 @@ void fill_dev_params(sf_solver* s)
     P.numBricks = s->numBricks;
     P.z0 = 0;
     P.nzGlobal = s->nS();
-    P.zDensLo = P.zForceLo = P.zOwnLo = 0;
-    P.zDensHi = P.zForceHi = P.zOwnHi = s->nS();
+    P.zDensLo = P.zShepLo = P.zForceLo = P.zOwnLo = 0;
+    P.zDensHi = P.zShepHi = P.zForceHi = P.zOwnHi = s->nS();
     P.zEdge = 0;
     P.slab  = 0;
     for(int w = 0; w < 6; ++w) P.nbnd[w] = P.useBoundary ? static_cast<uint32_t>(s->walls[w].size() / 3) : 0u;
@@ -421,7 +422,7 @@ int enqueue_substep_launches(sf_solver* s, const float* velHostXYZ = nullptr)
         }
         if(P.correctDensity) {
             LaunchScope ls(s, K_CORRECT_DENSITY);
-            k_correct_density<<<gridN, 256, 0, st>>>(B, P);
+            k_shepard_brick<<<std::min<uint32_t>(pairGrid, s->numSMs * s->occForce), kBrickThreads, kSmemPair, st>>>(B, P);
             k_density_terms<<<gridN, 256, 0, st>>>(B, P);
         }
         if(velHostXYZ) {
@@ -505,12 +506,13 @@ int require_ready(sf_solver* s)
 
 namespace
 {
-// P / sort plan / brick grid for the current cut planes: local window = own layers + kGhost on each side
+// P / sort plan / brick grid for the current cut planes: local window = own layers + L.ghost layers on each side
 int slab_configure_window(sf_solver* s)
 {
     sf_solver::Slab& L = s->slab;
     const int zb = L.cur[L.rank], ze = L.cur[L.rank + 1];
-    const int nzL = ze - zb + 2 * kGhost;
+    const int g   = L.ghost;
+    const int nzL = ze - zb + 2 * g;
     s->ncells    = static_cast<uint64_t>(s->grid[0]) * s->nM() * nzL;
     s->numBricks = static_cast<uint32_t>((s->grid[0] + BX - 1) / BX) * ((s->nM() + BY - 1) / BY) * ((nzL + BZ - 1) / BZ);
     fill_dev_params(s);
@@ -518,15 +520,20 @@ int slab_configure_window(sf_solver* s)
     P.nz        = nzL;
     P.nbz       = (nzL + BZ - 1) / BZ;
     P.numBricks = s->numBricks;
-    P.z0        = zb - kGhost;
+    P.z0        = zb - g;
     P.nzGlobal  = s->nS();
-    P.zDensLo = 1;
-    P.zDensHi = nzL - 1;
-    P.zForceLo = 2;
-    P.zForceHi = nzL - 2;
-    P.zOwnLo = kGhost;
-    P.zOwnHi = nzL - kGhost;
-    P.zEdge  = kEdge;
+    // every pass needs its neighbours' previous pass: density on all but the outermost ghost layer it needs, then
+    // (Shepard,) force, and the XSPH sum + integration on the own layers
+    const int dens = P.correctDensity ? g - 3 : g - 2;
+    P.zDensLo  = dens;
+    P.zDensHi  = nzL - dens;
+    P.zShepLo  = g - 2;
+    P.zShepHi  = nzL - (g - 2);
+    P.zForceLo = g - 1;
+    P.zForceHi = nzL - (g - 1);
+    P.zOwnLo = g;
+    P.zOwnHi = nzL - g;
+    P.zEdge  = slab_edge(g);
     P.slab   = 1;
     int bits = 1;
     while((1ull << bits) <= s->ncells) ++bits;
@@ -584,7 +591,7 @@ int slab_exchange(sf_solver* s, uint32_t n, uint32_t nSlots)
     SF_CUDA(s, cudaStreamWaitEvent(ms, L.evEdge, 0));
     SF_CUDA(s, cudaMemsetAsync(L.counters, 0, 2 * sizeof(uint32_t), ms));
     if(n) k_slab_pack<<<std::min<uint32_t>(cdiv(n, 256), 64), 256, 0, ms>>>(B.posA, B.velA, B.idA, L.layerStart, P, L.next[L.rank], L.next[L.rank + 1],
-                                                                               hasLower, hasUpper, L.sendLo, L.sendHi, L.sendCap, L.counters);
+                                                                               L.ghost, hasLower, hasUpper, L.sendLo, L.sendHi, L.sendCap, L.counters);
     k_slab_row<<<1, 1, 0, ms>>>(L.layerStart, L.counters, P, L.row);
     if(nc.AllGather(L.row, L.table, kRowWords, ncclUint32, L.comm, ms) != ncclSuccess) return fail(s, SF_ERR_COMM, "ncclAllGather failed");
     SF_CUDA(s, cudaMemcpyAsync(L.hostTable, L.table, sizeof(uint32_t) * kRowWords * L.nranks, cudaMemcpyDeviceToHost, ms));
@@ -603,7 +610,7 @@ int slab_exchange(sf_solver* s, uint32_t n, uint32_t nSlots)
         SF_CUDA(s, dev_alloc(L.sendHi, static_cast<size_t>(L.sendCap) * 2));
         SF_CUDA(s, cudaMemsetAsync(L.counters, 0, 2 * sizeof(uint32_t), ms));
         k_slab_pack<<<std::min<uint32_t>(cdiv(n, 256), 64), 256, 0, ms>>>(B.posA, B.velA, B.idA, L.layerStart, P, L.next[L.rank], L.next[L.rank + 1],
-                                                                            hasLower, hasUpper, L.sendLo, L.sendHi, L.sendCap, L.counters);
+                                                                            L.ghost, hasLower, hasUpper, L.sendLo, L.sendHi, L.sendCap, L.counters);
         L.regrowths++;
     }
     if(std::max(recvLo, recvHi) > L.recvCap) {
@@ -746,6 +753,7 @@ int sf_create(const sf_params* p, int device, sf_solver** out)
     if(e == cudaSuccess) e = cudaFuncSetAttribute(k_density_brick, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemDensity));
     if(e == cudaSuccess) e = cudaFuncSetAttribute(k_force_brick, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemPair));
     if(e == cudaSuccess) e = cudaFuncSetAttribute(k_visc_brick, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemPair));
+    if(e == cudaSuccess) e = cudaFuncSetAttribute(k_shepard_brick, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemPair));
     if(e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->occDensity, k_density_brick, kBrickThreads, kSmemDensity);
     if(e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->occForce, k_force_brick, kBrickThreads, kSmemPair);
     if(e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->occVisc, k_visc_brick, kBrickThreads, kSmemPair);
@@ -944,11 +952,12 @@ int sf_make_ready(sf_solver* s)
     params_update(s->params);
     build_tables(s->params.kernelRadius, s->tables);
     grid_dims(s->params, s->grid);
-    const int zPad = s->slab.on ? 2 * kGhost : 0; // slab mode: room for any window [zb - 3, ze + 3)
+    const int zPad = s->slab.on ? 2 * kGhostMax : 0; // slab mode: room for any window [zb - ghost, ze + ghost)
     if(!s->slab.on) s->axisS = 2;
     s->ncells = static_cast<uint64_t>(s->grid[0]) * s->nM() * (s->nS() + zPad);
     if(s->ncells == 0 || s->ncells >= (1ull << 31)) return fail(s, SF_ERR_INVALID, "grid has no cells or more than 2^31 cells");
-    if(s->slab.on && s->params.bCorrectDensity) return fail(s, SF_ERR_INVALID, "bCorrectDensity needs a fourth ghost layer: not supported with slabs");
+    if(s->slab.on && s->params.bCorrectDensity && s->slab.ghost < 4)
+        return fail(s, SF_ERR_INVALID, "bCorrectDensity needs a fourth ghost layer: set it before sf_upload_particles_global");
     if(s->slab.on && s->slab.cur.empty()) return fail(s, SF_ERR_INVALID, "slab mode: use sf_upload_particles_global");
     if(s->params.bUseBoundaryParticles && !s->wallsSet) {
         generate_boundary(s->params, 0u, s->walls); // the reference seeds from std::random_device; we default to seed 0
@@ -1853,6 +1862,8 @@ static int upload_particles_global(sf_solver* s, const float* pos_xyz, const flo
     L.next = L.cur;
     const int zb = L.cur[L.rank], ze = L.cur[L.rank + 1];
     uint64_t inWindow = 0; // particles of [zb - 3, ze + 3): from the layer histogram
+    L.ghost = s->params.bCorrectDensity ? 4 : 3;
+    const int kGhost = L.ghost;
     for(int l = std::max(zb - kGhost, 0); l < std::min(ze + kGhost, s->nS()); ++l) inWindow += hist[l];
     if(inWindow > 0xfffffff0ull) return fail(s, SF_ERR_OOM, "more than 2^32 particles on one rank");
     std::vector<float>    hp(3 * inWindow), hv(vel_xyz ? 3 * inWindow : 0);
@@ -1876,7 +1887,7 @@ static int upload_particles_global(sf_solver* s, const float* pos_xyz, const flo
     SF_CUDA(s, dev_alloc(L.sendHi, static_cast<size_t>(L.sendCap) * 2));
     SF_CUDA(s, dev_alloc(L.recvLo, static_cast<size_t>(L.recvCap) * 2));
     SF_CUDA(s, dev_alloc(L.recvHi, static_cast<size_t>(L.recvCap) * 2));
-    SF_CUDA(s, dev_alloc(L.layerStart, static_cast<size_t>(std::max(g[1], g[2])) + 2 * kGhost + 2));
+    SF_CUDA(s, dev_alloc(L.layerStart, static_cast<size_t>(std::max(g[1], g[2])) + 2 * kGhostMax + 2));
     if(n) {
         float*    dpos = s->stage;
         float*    dvel = s->stage + 3 * static_cast<size_t>(s->npad);

@@ -41,6 +41,7 @@ struct DevParams {
     // number of cell layers; local layer l is global layer l + z0 (z0 may be negative at the bottom slab).
     int      z0, nzGlobal;
     int      zDensLo, zDensHi;   // local layers whose particles get a density / list
+    int      zShepLo, zShepHi;   // ... a Shepard-corrected density (bCorrectDensity only)
     int      zForceLo, zForceHi; // ... a pressure force and v*
     int      zOwnLo, zOwnHi;     // ... are integrated (owned by this rank)
     int      zEdge;              // own layers within zEdge of a slab face are "boundary" for the overlapped exchange
@@ -66,7 +67,7 @@ struct DevState {
     unsigned nbrMax;      // largest neighbour count seen (diagnostics)
     unsigned long long stepsDone;
     unsigned brickCount;  // non-empty bricks of this substep
-    unsigned cursor[4];   // work cursors of the persistent pair kernels (density, force, viscosity)
+    unsigned cursor[6];   // work cursors of the persistent pair kernels (density, force, viscosity edge / interior, Shepard)
     unsigned fallbackBricks, fallbackParticles; // diagnostics: halos that did not fit smem / lists that overflowed
 };
 

@@ -84,7 +84,7 @@ __global__ void k_begin_step(DevState* st, DevParams P, int phases)
         }
         st->skip          = 0;
         st->brickCount    = 0u;
-        st->cursor[0] = st->cursor[1] = st->cursor[2] = st->cursor[3] = 0u;
+        st->cursor[0] = st->cursor[1] = st->cursor[2] = st->cursor[3] = st->cursor[4] = st->cursor[5] = 0u;
     }
     if(!(phases & kBeginClock) || st->skip) return;
     const unsigned pr = st->step & 1u;

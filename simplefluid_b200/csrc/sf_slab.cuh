@@ -24,8 +24,8 @@
 
 namespace sf
 {
-constexpr int kGhost   = 3; // ghost layers per side
-constexpr int kEdge    = 5; // own layers per side whose particles may have to be exchanged (kGhost + movement + cut shift)
+constexpr int kGhostMax = 4; // ghost layers per side: 3 (density, force, XSPH), 4 with bCorrectDensity (+ Shepard pass)
+inline int slab_edge(int ghost) { return ghost + 2; } // own layers per side whose particles may have to be exchanged (ghost + movement + cut shift)
 constexpr int kMinThick = 6; // minimum slab thickness in layers
 constexpr int kRowWords = 8;
 
@@ -94,7 +94,7 @@ __global__ void k_fill_u32(uint32_t* __restrict__ a, uint32_t n, uint32_t v)
 // Pack the freshly integrated own particles near the slab faces for the neighbours.  zbN/zeN = NEXT bounds (global).
 // send buffers: 2 float4 per particle {x, y, z, id bits}, {vx, vy, vz, 0}.  counters[0/1] = lower/upper count.
 __global__ void k_slab_pack(const float4* __restrict__ posA, const float4* __restrict__ velA, const uint32_t* __restrict__ idA,
-                            const uint32_t* __restrict__ layerStart, DevParams P, int zbN, int zeN, int hasLower, int hasUpper,
+                            const uint32_t* __restrict__ layerStart, DevParams P, int zbN, int zeN, int ghost, int hasLower, int hasUpper,
                             float4* __restrict__ sendLo, float4* __restrict__ sendHi, uint32_t cap, uint32_t* __restrict__ counters)
 {
     const uint32_t ownB = layerStart[P.zOwnLo], ownE = layerStart[P.zOwnHi];
@@ -108,14 +108,14 @@ __global__ void k_slab_pack(const float4* __restrict__ posA, const float4* __res
         const float4 x  = posA[p];
         const float4 v  = velA[p];
         const int    cz = cell_layer_global(P, x);
-        if(hasLower && cz < zbN + kGhost) {
+        if(hasLower && cz < zbN + ghost) {
             const uint32_t k = atomicAdd(&counters[0], 1u);
             if(k < cap) {
                 sendLo[2 * k]     = make_float4(x.x, x.y, x.z, __uint_as_float(id));
                 sendLo[2 * k + 1] = make_float4(v.x, v.y, v.z, 0.f);
             }
         }
-        if(hasUpper && cz >= zeN - kGhost) {
+        if(hasUpper && cz >= zeN - ghost) {
             const uint32_t k = atomicAdd(&counters[1], 1u);
             if(k < cap) {
                 sendHi[2 * k]     = make_float4(x.x, x.y, x.z, __uint_as_float(id));

@@ -26,6 +26,8 @@ def _ngpu():
     (2, "Dambreak", 32, 200, {}, "host_owned"),                     # sf_step_host_owned: owned particles live on the host
     (2, "Dambreak", 32, 200, {"SF_SLAB_TIGHT": "1"}, "host_owned"),
     (2, "DoubleDambreak", 40, 160, {}, "checkpoint"),               # per-rank checkpoint parts, restored on 2 ranks and on 1
+    (2, "Dambreak", 32, 250, {"SF_TEST_PARAMS": "bCorrectDensity=1"}, "resident"),  # Shepard pass: four ghost layers per side
+    (2, "CubeDrop", 24, 400, {"SF_TEST_PARAMS": "bCorrectDensity=1,bUseAttractivePressure=1", "SF_SLAB_AXIS": "y"}, "resident"),
 ])
 def test_slabs_bit_identical_to_single_gpu(sf, world, scene, res, steps, env, mode):
     if _ngpu() < world:

@@ -25,7 +25,8 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     uid = [binding.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
-    p = sf.default_params(res, scene)
+    over = {k: int(v) for k, v in (kv.split("=") for kv in os.environ.get("SF_TEST_PARAMS", "").split(",") if kv)}  # e.g. bCorrectDensity=1
+    p = sf.default_params(res, scene, **over)
     pos = sf.scene_generate(p)
     g = sf.SPHSolver(p, device=local)
     g.commInit(rank, world, uid[0])
