@@ -485,6 +485,10 @@ int read_state(sf_solver* s)
 {
     SF_CUDA(s, cudaMemcpyAsync(s->hostState, s->B.state, sizeof(DevState), cudaMemcpyDeviceToHost, s->stream));
     SF_CUDA(s, cudaStreamSynchronize(s->stream));
+    if(s->hostState->errFlags & SF_DEVERR_DOMAIN) {
+        cudaMemsetAsync(&s->B.state->errFlags, 0, sizeof(unsigned), s->stream);
+        return fail(s, SF_ERR_DOMAIN, "a particle of the host buffer lies outside the simulation box or is not finite");
+    }
     if(s->hostState->errFlags) {
         char buf[256];
         std::snprintf(buf, sizeof(buf),
@@ -1176,7 +1180,7 @@ int sf_step_host(sf_solver* s, float* pos_xyz, float* vel_xyz, uint32_t n, float
         SF_CUDA(s, cudaStreamWaitEvent(cs, s->evPosUp, 0));
         {
             LaunchScope ls(s, K_MARSHAL);
-            k_pack_pos<<<cdiv(n, 256), 256, 0, cs>>>(dpos, s->B.posA, s->B.idA, n);
+            k_pack_pos<<<cdiv(n, 256), 256, 0, cs>>>(dpos, s->B.posA, s->B.idA, n, s->P, s->B.state);
         }
         rc = enqueue_substep_launches(s, dvel);
         if(rc) return rc;

@@ -71,7 +71,7 @@ struct DevState {
     unsigned fallbackBricks, fallbackParticles; // diagnostics: halos that did not fit smem / lists that overflowed
 };
 
-enum : unsigned { SF_DEVERR_NBR_OVERFLOW = 1u, SF_DEVERR_WALL_OVERFLOW = 2u };
+enum : unsigned { SF_DEVERR_NBR_OVERFLOW = 1u, SF_DEVERR_WALL_OVERFLOW = 2u, SF_DEVERR_DOMAIN = 4u };
 
 struct DevBuffers {
     float4 *posA, *velA, *posB, *velB;

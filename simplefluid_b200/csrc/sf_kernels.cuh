@@ -468,11 +468,28 @@ __global__ void k_gather_vel_host(const float* __restrict__ velXYZ, const uint32
     if((threadIdx.x & 31) == 0 && m > FLT_MIN) atomicMax(&st->maxv2Bits[st->step & 1u], __float_as_uint(m));
 }
 
-__global__ void k_pack_pos(const float* __restrict__ posXYZ, float4* __restrict__ pos, uint32_t* __restrict__ id, uint32_t n)
+// the host's cell_coords_checked (sf_host.cpp) with the same float ops: inside the box on every axis, finite
+__device__ __forceinline__ bool in_box(const DevParams& P, float x, float y, float z)
+{
+    const float c[3] = { x, y, z };
+    const int   g[3] = { P.nx, P.axisS == 1 ? P.nzGlobal : P.ny, P.axisS == 2 ? P.nzGlobal : P.ny };
+    for(int d = 0; d < 3; ++d) {
+        const float t = (c[d] - P.bmin[d]) / P.h;
+        if(!(t >= 0.0f) || !(t < static_cast<float>(g[d]))) return false; // also rejects NaN / inf
+    }
+    return true;
+}
+
+// sf_step_host, steady state: positions from the uploaded xyz array, id = upload index.  Validates the domain like
+// sf_upload_particles does on the host (SF_DEVERR_DOMAIN -> SF_ERR_DOMAIN): the pair loops assume that a particle's
+// unclamped cell equals its binned cell.
+__global__ void k_pack_pos(const float* __restrict__ posXYZ, float4* __restrict__ pos, uint32_t* __restrict__ id, uint32_t n, DevParams P, DevState* st)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if(i >= n) return;
-    pos[i] = make_float4(posXYZ[3 * i], posXYZ[3 * i + 1], posXYZ[3 * i + 2], 0.f);
+    const float x = posXYZ[3 * static_cast<size_t>(i)], y = posXYZ[3 * static_cast<size_t>(i) + 1], z = posXYZ[3 * static_cast<size_t>(i) + 2];
+    if(!in_box(P, x, y, z)) atomicOr(&st->errFlags, SF_DEVERR_DOMAIN);
+    pos[i] = make_float4(x, y, z, 0.f);
     id[i]  = i;
 }
 

@@ -153,17 +153,6 @@ __global__ void k_slab_unpack(const float4* __restrict__ recv, uint32_t count, f
 // between substeps; the ghost particles of the next substep stay resident (they came with the last exchange).
 // counters: [0] = resident owned particles dropped, [1] = uploaded particles outside the box or this rank's layers,
 // [2] = owned particles gathered.
-__device__ __forceinline__ bool slab_in_box(const DevParams& P, float x, float y, float z)
-{
-    const float c[3] = { x, y, z };
-    const int   g[3] = { P.nx, P.axisS == 1 ? P.nzGlobal : P.ny, P.axisS == 2 ? P.nzGlobal : P.ny };
-    for(int d = 0; d < 3; ++d) { // the host's cell_coords_checked (sf_host.cpp), same float ops
-        const float t = (c[d] - P.bmin[d]) / P.h;
-        if(!(t >= 0.0f) || !(t < static_cast<float>(g[d]))) return false; // also rejects NaN / inf
-    }
-    return true;
-}
-
 __global__ void k_owned_reset_maxvel(DevState* st) { st->maxv2Bits[st->step & 1u] = __float_as_uint(FLT_MIN); }
 
 // the resident copies of this rank's own particles give way to the host's
@@ -194,7 +183,7 @@ __global__ void k_owned_append(const float* __restrict__ posXYZ, const float* __
         const float4 x = make_float4(posXYZ[3 * static_cast<size_t>(i)], posXYZ[3 * static_cast<size_t>(i) + 1], posXYZ[3 * static_cast<size_t>(i) + 2], 0.f);
         const float4 v = make_float4(velXYZ[3 * static_cast<size_t>(i)], velXYZ[3 * static_cast<size_t>(i) + 1], velXYZ[3 * static_cast<size_t>(i) + 2], 0.f);
         const int    cz = cell_layer_global(P, x);
-        if(!slab_in_box(P, x.x, x.y, x.z) || cz < zb || cz >= ze) ++bad;
+        if(!in_box(P, x.x, x.y, x.z) || cz < zb || cz >= ze) ++bad;
         pos[i] = x;
         vel[i] = v;
         id[i]  = ids[i];

@@ -242,6 +242,28 @@ def test_host_buffer_step_roundtrip(sf, ob):
     orc.close()
 
 
+def test_host_buffer_step_validates_the_domain_every_call(sf):
+    """The steady-state path of sf_step_host (same particle count as the previous call) checks the box on the device:
+    an out-of-box or non-finite position is SF_ERR_DOMAIN, as in sf_upload_particles -- not a silently wrong step."""
+    p = sf.default_params(24, "SphereDrop")
+    pos = sf.scene_generate(p)
+    gpu = sf.SPHSolver(p)
+    gpu.generateBoundaryParticles(0)
+    x, v = pos.copy(), np.zeros_like(pos)
+    gpu.stepHost(x, v)
+    gpu.stepHost(x, v)  # steady path
+    for bad in (np.float32(1.5), np.float32(np.nan)):
+        xb = x.copy()
+        xb[17, 1] = bad
+        with pytest.raises(sf.SFError) as e:
+            gpu.stepHost(xb, v.copy())
+        assert e.value.code == -3
+    x2, v2 = x.copy(), v.copy()
+    gpu.stepHost(x2, v2)  # and the solver keeps working afterwards
+    assert np.isfinite(x2).all()
+    gpu.close()
+
+
 def test_edge_cases_empty_single_and_rejects(sf, ob):
     p = sf.default_params(24, "Dambreak")
     gpu = sf.SPHSolver(p)
