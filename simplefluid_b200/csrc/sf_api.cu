@@ -101,6 +101,13 @@ struct sf_solver {
         uint64_t             ncellsMax = 0;
         uint64_t             exchangedParticles = 0;
         double               tWaitPack = 0, tPost = 0, tFront = 0; // host seconds: waiting for the table / posting the exchange / enqueueing
+        double               tGroup = 0, tReduce = 0; // ... of which: the send/recv group, the dt all-reduce
+        // SF_SLAB_TRACE=2: device-side timeline of the last kTlSteps substeps (CUDA events; printed at destruction):
+        // 0 step start, 1 sort + reorder done, 2 density done, 3 dt known, 4 force done on the edge layers, 5 edge layers
+        // integrated, 6 interior layers done (compute stream); 7 table gathered, 8 exchange done (communication stream)
+        static constexpr int kTlSteps = 64, kTlMarks = 9;
+        std::vector<cudaEvent_t> tl;
+        int                      tlLevel = 0;
         uint64_t             steps = 0;
         // global dt: the all-reduce of max |v|^2 runs on the communication stream behind the exchange and is awaited
         // only before the force pass of the next substep (dtReduced: evDt covers the current maxv2Bits)
@@ -128,6 +135,52 @@ void drop_graph(sf_solver* s)
     if(s->stepGraph) {
         cudaGraphExecDestroy(s->stepGraph);
         s->stepGraph = nullptr;
+    }
+}
+
+void tl_mark(sf_solver* s, int mark, cudaStream_t st)
+{
+    sf_solver::Slab& L = s->slab;
+    if(L.tlLevel < 2) return;
+    if(L.tl.empty()) {
+        L.tl.resize(static_cast<size_t>(L.kTlSteps) * L.kTlMarks);
+        for(auto& e : L.tl) cudaEventCreate(&e);
+    }
+    cudaEventRecord(L.tl[static_cast<size_t>(L.steps % L.kTlSteps) * L.kTlMarks + mark], st);
+}
+
+void slab_timeline_report(sf_solver* s)
+{
+    sf_solver::Slab& L = s->slab;
+    if(!L.tl.empty() && L.steps > static_cast<uint64_t>(L.kTlSteps)) {
+        // mean intervals over the recorded ring (skipping the step the ring currently points at)
+        const char* names[] = { "sort+reorder", "density", "wait dt (all-reduce)", "force (edge layers)", "integrate (edge layers)", "force + integrate (interior layers)",
+                                "edge->table gathered (comm)", "table->exchange done (comm, incl. host turn-around)",
+                                "interior done->next step start (compute stream idle)", "exchange done->next step start" };
+        double acc[10] = {};
+        int    cnt = 0;
+        auto ms = [&](int stepA, int a, int stepB, int b) {
+            float t = 0.f;
+            cudaEventElapsedTime(&t, L.tl[static_cast<size_t>(stepA) * L.kTlMarks + a], L.tl[static_cast<size_t>(stepB) * L.kTlMarks + b]);
+            return static_cast<double>(t);
+        };
+        const int cur = static_cast<int>(L.steps % L.kTlSteps);
+        for(int k = 0; k < L.kTlSteps - 2; ++k) {
+            const int a = (cur + 1 + k) % L.kTlSteps, b = (a + 1) % L.kTlSteps; // a older than b, both complete
+            for(int i = 0; i < 6; ++i) acc[i] += ms(a, i, a, i + 1);
+            acc[6] += ms(a, 5, a, 7);
+            acc[7] += ms(a, 7, a, 8);
+            acc[8] += ms(a, 6, b, 0);
+            acc[9] += ms(a, 8, b, 0);
+            ++cnt;
+        }
+        std::string line = "[sf slab rank " + std::to_string(L.rank) + "] device timeline, mean ms over " + std::to_string(cnt) + " substeps:";
+        for(int i = 0; i < 10; ++i) {
+            char buf[128];
+            std::snprintf(buf, sizeof(buf), " %s %.3f;", names[i], acc[i] / cnt);
+            line += buf;
+        }
+        std::fprintf(stderr, "%s\n", line.c_str());
     }
 }
 
@@ -331,6 +384,7 @@ int enqueue_substep_launches(sf_solver* s, const float* velHostXYZ = nullptr)
     // awaited only before the force pass: sorting and the density pass need no dt, so the skew between ranks -- every
     // rank would otherwise wait here for the slowest one to finish integrating -- hides behind them.
     const bool splitClock = velHostXYZ != nullptr || slab;
+    if(slab) tl_mark(s, 0, st);
     {
         LaunchScope ls(s, K_BEGIN);
         k_begin_step<<<1, 1, 0, st>>>(B.state, P, splitClock ? kBeginResets : kBeginAll);
@@ -416,10 +470,12 @@ int enqueue_substep_launches(sf_solver* s, const float* velHostXYZ = nullptr)
             if(velHostXYZ) k_reorder_pos<<<gridN, 256, 0, st>>>(B.keyB, B.vals[cur], B.cellTab, B.posA, B.idA, B.posB, B.idB, n, B.state);
             else k_reorder<<<gridN, 256, 0, st>>>(B.keyB, B.vals[cur], B.cellTab, B.posA, B.velA, B.idA, B.posB, B.velB, B.idB, n, B.state);
         }
+        if(slab) tl_mark(s, 1, st);
         {
             LaunchScope ls(s, K_DENSITY);
             k_density_brick<<<std::min<uint32_t>(pairGrid, s->numSMs * s->occDensity), kBrickThreads, kSmemDensity, st>>>(B, P);
         }
+        if(slab) tl_mark(s, 2, st);
         if(P.correctDensity) {
             LaunchScope ls(s, K_CORRECT_DENSITY);
             k_shepard_brick<<<std::min<uint32_t>(pairGrid, s->numSMs * s->occForce), kBrickThreads, kSmemPair, st>>>(B, P);
@@ -435,13 +491,15 @@ int enqueue_substep_launches(sf_solver* s, const float* velHostXYZ = nullptr)
     if(slab) {
         const int rc = slab_global_dt(s);
         if(rc) return rc;
+        tl_mark(s, 3, st);
     }
     if(n) {
-        {
+        {   // slab mode: the layers near the slab faces first; the interior layers follow the edge integrate (slab_exchange)
             LaunchScope ls(s, K_FORCE);
-            k_force_brick<<<std::min<uint32_t>(pairGrid, s->numSMs * s->occForce), kBrickThreads, kSmemPair, st>>>(B, P);
+            k_force_brick<<<std::min<uint32_t>(pairGrid, s->numSMs * s->occForce), kBrickThreads, kSmemPair, st>>>(B, P, slab ? 1 : 0);
         }
     }
+    if(slab) tl_mark(s, 4, st);
     if(!slab) {
         LaunchScope ls(s, K_VISC_INTEGRATE);
         k_visc_brick<<<std::min<uint32_t>(pairGrid, s->numSMs * s->occVisc), kBrickThreads, kSmemPair, st>>>(B, P, 0);
@@ -584,12 +642,20 @@ int slab_exchange(sf_solver* s, uint32_t n, uint32_t nSlots)
         k_visc_brick<<<std::min<uint32_t>(pairGrid, s->numSMs * s->occVisc), kBrickThreads, kSmemPair, cs>>>(B, P, 1);
     }
     SF_CUDA(s, cudaEventRecord(L.evEdge, cs));
-    if(n) { // interior bricks: leave a few CTA slots free so that the pack / NCCL kernels can run beside them
+    tl_mark(s, 5, cs);
+    static const int freeSlots = std::getenv("SF_SLAB_FREE_SLOTS") ? std::max(0, std::atoi(std::getenv("SF_SLAB_FREE_SLOTS"))) : 4;
+    if(n) { // interior layers: force, then integrate; a few CTA slots stay free so that the pack / NCCL kernels can run beside them
+        {
+            LaunchScope    ls(s, K_FORCE);
+            const uint32_t g = std::min<uint32_t>(pairGrid, s->numSMs * s->occForce);
+            k_force_brick<<<g > 32 ? g - std::min<uint32_t>(freeSlots, g - 1) : g, kBrickThreads, kSmemPair, cs>>>(B, P, 2);
+        }
         LaunchScope    ls(s, K_VISC_INTEGRATE);
         const uint32_t g = std::min<uint32_t>(pairGrid, s->numSMs * s->occVisc);
-        k_visc_brick<<<g > 32 ? g - 4 : g, kBrickThreads, kSmemPair, cs>>>(B, P, 2);
+        k_visc_brick<<<g > 32 ? g - std::min<uint32_t>(freeSlots, g - 1) : g, kBrickThreads, kSmemPair, cs>>>(B, P, 2);
     }
     SF_CUDA(s, cudaEventRecord(L.evInterior, cs));
+    tl_mark(s, 6, cs);
     // ---- communication stream
     const int hasLower = L.rank > 0, hasUpper = L.rank < L.nranks - 1;
     SF_CUDA(s, cudaStreamWaitEvent(ms, L.evEdge, 0));
@@ -599,6 +665,7 @@ int slab_exchange(sf_solver* s, uint32_t n, uint32_t nSlots)
     k_slab_row<<<1, 1, 0, ms>>>(L.layerStart, L.counters, P, L.row);
     if(nc.AllGather(L.row, L.table, kRowWords, ncclUint32, L.comm, ms) != ncclSuccess) return fail(s, SF_ERR_COMM, "ncclAllGather failed");
     SF_CUDA(s, cudaMemcpyAsync(L.hostTable, L.table, sizeof(uint32_t) * kRowWords * L.nranks, cudaMemcpyDeviceToHost, ms));
+    tl_mark(s, 7, ms);
     const auto tw0 = std::chrono::steady_clock::now();
     SF_CUDA(s, cudaStreamSynchronize(ms)); // the compute stream keeps integrating the interior bricks meanwhile
     const auto tw1 = std::chrono::steady_clock::now();
@@ -632,6 +699,7 @@ int slab_exchange(sf_solver* s, uint32_t n, uint32_t nSlots)
         if(rc) return rc;
         L.regrowths++;
     }
+    const auto tg0 = std::chrono::steady_clock::now();
     if(nc.GroupStart() != ncclSuccess) return fail(s, SF_ERR_COMM, "ncclGroupStart failed");
     ncclResult_t r = ncclSuccess;
     if(hasLower) {
@@ -643,15 +711,19 @@ int slab_exchange(sf_solver* s, uint32_t n, uint32_t nSlots)
         if(recvHi && r == ncclSuccess) r = nc.Recv(L.recvHi, static_cast<size_t>(recvHi) * 8, ncclFloat, L.rank + 1, L.comm, ms);
     }
     if(nc.GroupEnd() != ncclSuccess || r != ncclSuccess) return fail(s, SF_ERR_COMM, "halo send/recv failed");
+    L.tGroup += std::chrono::duration<double>(std::chrono::steady_clock::now() - tg0).count();
     if(recvLo) k_slab_unpack<<<cdiv(recvLo, 256), 256, 0, ms>>>(L.recvLo, recvLo, B.posA + n, B.velA + n, B.idA + n);
     if(recvHi) k_slab_unpack<<<cdiv(recvHi, 256), 256, 0, ms>>>(L.recvHi, recvHi, B.posA + n + recvLo, B.velA + n + recvLo, B.idA + n + recvLo);
     SF_CUDA(s, cudaEventRecord(L.evExchanged, ms));
+    tl_mark(s, 8, ms);
     SF_CUDA(s, cudaStreamWaitEvent(cs, L.evExchanged, 0));
     // max |v|^2 of this substep is complete once the interior bricks are integrated: reduce it over the ranks on the
     // communication stream; the next substep waits for it only before its force pass (slab_global_dt)
     SF_CUDA(s, cudaStreamWaitEvent(ms, L.evInterior, 0));
+    const auto tr0 = std::chrono::steady_clock::now();
     if(nc.AllReduce(B.state->maxv2Bits, B.state->maxv2Bits, 2, ncclUint32, ncclMax, L.comm, ms) != ncclSuccess)
         return fail(s, SF_ERR_COMM, "ncclAllReduce(max |v|^2) failed");
+    L.tReduce += std::chrono::duration<double>(std::chrono::steady_clock::now() - tr0).count();
     SF_CUDA(s, cudaEventRecord(L.evDt, ms));
     L.dtReduced = true;
     SF_CUDA(s, cudaGetLastError());
@@ -811,10 +883,12 @@ void sf_destroy(sf_solver* s)
     {
         sf_solver::Slab& L = s->slab;
         if(L.on && L.steps && std::getenv("SF_SLAB_TRACE"))
-            std::fprintf(stderr, "[sf slab rank %d] %llu substeps: host wait for edge+pack+allgather %.3f ms/step, post exchange %.3f ms/step, exchanged %.1f particles/step, %llu capacity regrowths, axis %c\n",
-                         L.rank, (unsigned long long)L.steps, L.tWaitPack / L.steps * 1e3, L.tPost / L.steps * 1e3, double(L.exchangedParticles) / L.steps,
+            std::fprintf(stderr, "[sf slab rank %d] %llu substeps: host wait for edge+pack+allgather %.3f ms/step, post exchange %.3f ms/step (send/recv group %.3f, dt all-reduce %.3f), exchanged %.1f particles/step, %llu capacity regrowths, axis %c\n",
+                         L.rank, (unsigned long long)L.steps, L.tWaitPack / L.steps * 1e3, L.tPost / L.steps * 1e3, L.tGroup / L.steps * 1e3, L.tReduce / L.steps * 1e3, double(L.exchangedParticles) / L.steps,
                          (unsigned long long)L.regrowths, s->axisS == 1 ? 'y' : 'z');
         if(L.commStream) cudaStreamSynchronize(L.commStream); // the last substep's dt all-reduce may still be in flight
+        slab_timeline_report(s);
+        for(auto& e : L.tl) cudaEventDestroy(e);
         if(L.comm && nccl_api().CommDestroy) nccl_api().CommDestroy(L.comm);
         cudaFree(L.sendLo); cudaFree(L.sendHi); cudaFree(L.recvLo); cudaFree(L.recvHi);
         cudaFree(L.layerStart); cudaFree(L.counters); cudaFree(L.row); cudaFree(L.table);
@@ -1529,6 +1603,7 @@ int sf_timer_stop(sf_solver* s, float* ms_out)
     SF_CUDA(s, cudaEventRecord(s->timerB, s->stream));
     SF_CUDA(s, cudaEventSynchronize(s->timerB));
     SF_CUDA(s, cudaEventElapsedTime(ms_out, s->timerA, s->timerB));
+    if(s->slab.on && s->slab.tlLevel >= 2) slab_timeline_report(s); // SF_SLAB_TRACE=2: the region just timed
     return SF_OK;
 }
 
@@ -1809,6 +1884,7 @@ int sf_comm_init(sf_solver* s, int rank, int nranks, const void* id128)
     L.on     = true;
     L.rank   = rank;
     L.nranks = nranks;
+    if(const char* t = std::getenv("SF_SLAB_TRACE")) L.tlLevel = std::atoi(t);
     int lo = 0, hi = 0;
     SF_CUDA(s, cudaDeviceGetStreamPriorityRange(&lo, &hi));
     SF_CUDA(s, cudaStreamCreateWithPriority(&L.commStream, cudaStreamNonBlocking, hi));
