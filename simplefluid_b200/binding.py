@@ -28,7 +28,7 @@ EXPORTS = [
     "sf_slab_plan", "sf_slab_rebalance", "sf_cell_layers", "sf_download_local", "sf_upload_local",
     "sf_snapshot_positions_async", "sf_snapshot_wait", "sf_checkpoint_write", "sf_checkpoint_read",
     "sf_host_alloc", "sf_host_free", "sf_diagnostics", "sf_set_list_capacity",
-    "sf_slab_axis", "sf_step_host_owned", "sf_checkpoint_read_slab",
+    "sf_slab_axis", "sf_step_host_owned", "sf_checkpoint_read_slab", "sf_debug_counters",
 ]
 
 
@@ -110,7 +110,7 @@ def library():
         "sf_checkpoint_write": [vp, C.c_char_p, f32], "sf_checkpoint_read": [C.c_char_p, C.c_int, C.POINTER(vp), C.POINTER(f32)],
         "sf_host_alloc": [u64, C.POINTER(vp)], "sf_host_free": [vp],
         "sf_diagnostics": [vp, vp], "sf_set_list_capacity": [vp, C.c_int],
-        "sf_slab_axis": [vp, C.POINTER(i32)],
+        "sf_slab_axis": [vp, C.POINTER(i32)], "sf_debug_counters": [vp, vp],
         "sf_step_host_owned": [vp, vp, vp, vp, u32, u32, C.POINTER(u32), C.POINTER(f32)],
         "sf_checkpoint_read_slab": [C.c_char_p, C.c_int, C.c_int, C.c_int, vp, C.POINTER(vp), C.POINTER(f32)],
         "sf_slab_plan": [vp, i32, i32, vp], "sf_slab_rebalance": [vp, i32, i32, vp], "sf_cell_layers": [PP, vp, u32, vp],
@@ -392,6 +392,11 @@ class SPHSolver:
 
     def setListCapacity(self, kmax):
         self._ck(self.L.sf_set_list_capacity(self.h, int(kmax)))
+
+    def debugCounters(self):
+        out = (C.c_uint64 * 4)()
+        self._ck(self.L.sf_debug_counters(self.h, out))
+        return [int(x) for x in out]
 
     def diagnostics(self):
         out = (C.c_uint64 * 8)()

@@ -1295,6 +1295,18 @@ int sf_host_free(void* p)
     return SF_OK;
 }
 
+int sf_debug_counters(sf_solver* s, uint64_t out[4])
+{
+    int rc = require_ready(s);
+    if(rc) return rc;
+    if(!out) return SF_ERR_INVALID;
+    SF_CUDA(s, cudaSetDevice(s->device));
+    rc = read_state(s);
+    if(rc) return rc;
+    for(int i = 0; i < 4; ++i) out[i] = s->hostState->dbg[i];
+    return SF_OK;
+}
+
 int sf_set_list_capacity(sf_solver* s, int kmax)
 {
     if(!s || kmax < 8 || kmax > 16383) return SF_ERR_INVALID;

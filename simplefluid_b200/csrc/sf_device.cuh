@@ -69,6 +69,7 @@ struct DevState {
     unsigned brickCount;  // non-empty bricks of this substep
     unsigned cursor[6];   // work cursors of the persistent pair kernels (density, force, viscosity edge / interior, Shepard)
     unsigned fallbackBricks, fallbackParticles; // diagnostics: halos that did not fit smem / lists that overflowed
+    unsigned long long dbg[4]; // SF_EXP_WAITSTAT builds: warp cycles of the density pass spent waiting for a brick / filtering / in the exact phase / total
 };
 
 enum : unsigned { SF_DEVERR_NBR_OVERFLOW = 1u, SF_DEVERR_WALL_OVERFLOW = 2u, SF_DEVERR_DOMAIN = 4u };

@@ -35,4 +35,7 @@ h = hashlib.sha256(g.getParticles().tobytes() + g.getVelocity().tobytes()).hexdi
 print(f"{os.path.basename(sf.library_path())}: {scene} res {res} N={len(pos)} at rest {ms_rest / steps:.3f} ms/step, developed {ms / steps:.3f} ms/step "
       f"= {len(pos) * steps / ms * 1e3:.3e} p-steps/s; fallback bricks {d['fallback_bricks']} nbr_mean {d['nbr_mean']:.1f} state {h}")
 print("   " + "  ".join(f"{k[2:]}={t / c:.3f}" for k, (t, c) in prof.items() if c))
+dbg = g.debugCounters()
+if dbg[3]:
+    print(f"   density consumer warps: waiting for a brick {dbg[0] / dbg[3] * 100:.1f} %, exact phase {dbg[2] / dbg[3] * 100:.1f} % of their cycles")
 g.close()
