@@ -262,16 +262,23 @@ void slab_rebalance(const uint32_t* table, int32_t rowWords, int32_t nranks, int
 {
     (void)nz;
     std::vector<int32_t> old(cuts, cuts + nranks + 1);
+    bool lostBottom = false; // did the slab above the previous cut (= the lower slab of this one) just lose its bottom layer?
     for(int32_t b = 1; b < nranks; ++b) {
         const uint32_t* lower = table + static_cast<size_t>(b - 1) * rowWords;
         const uint32_t* upper = table + static_cast<size_t>(b) * rowWords;
         const int64_t   A = lower[2], Bc = upper[2];
         const int64_t   topA = lower[4], botB = upper[3];
         const int32_t   thickA = old[b] - old[b - 1], thickB = old[b + 1] - old[b];
-        // moving one layer changes the difference by twice that layer's population: move only past that hysteresis,
-        // and never let a slab lose two layers in one substep
-        if(A > Bc + 2 * topA && thickA > minThick + 1) cuts[b] = old[b] - 1;
-        else if(Bc > A + 2 * botB && thickB > minThick + 1) cuts[b] = old[b] + 1;
+        // moving one layer changes the difference by twice that layer's population: move only past that hysteresis.
+        // A slab never loses two layers in one substep: cuts are decided bottom-up, and a slab that has just given
+        // its bottom layer to the slab below keeps its top layer for this substep.
+        bool upperLosesBottom = false;
+        if(A > Bc + 2 * topA && thickA > minThick + 1 && !lostBottom) cuts[b] = old[b] - 1;
+        else if(Bc > A + 2 * botB && thickB > minThick + 1) {
+            cuts[b]          = old[b] + 1;
+            upperLosesBottom = true;
+        }
+        lostBottom = upperLosesBottom;
     }
 }
 

@@ -64,13 +64,21 @@ def test_rebalance_rule_moves_one_layer_with_hysteresis(sf):
     thin = np.array([0, 6, 32, 48, 64], np.int32)
     out = binding.slab_rebalance(table([500, 100, 100, 100], [10] * 4, [10] * 4), nz, thin)
     assert out[1] == 6
-    # every plane moves by at most one layer per substep and slabs stay >= 6 layers
+    # a heavy middle slab between two light ones would give a layer to BOTH neighbours: it gives its bottom layer only
+    # (cuts are decided bottom-up), so no slab loses two layers in one substep
+    mid = np.array([0, 20, 28, 44, 64], np.int32)  # slab 1 is 8 layers thick (minimum 6)
+    out = binding.slab_rebalance(table([100, 900, 100, 100], [10] * 4, [10] * 4), nz, mid)
+    assert out.tolist() == [0, 21, 28, 44, 64]
+    out2 = binding.slab_rebalance(table([100, 900, 100, 100], [10] * 4, [10] * 4), nz, out)
+    assert out2.tolist() == out.tolist()  # 7 layers left: a slab only shrinks while it keeps more than the minimum + 1
+    # every plane moves by at most one layer per substep, slabs stay >= 6 layers and never lose two layers at once
     rng = np.random.default_rng(0)
     c = cuts.copy()
     for _ in range(200):
         own = rng.integers(0, 1000, 4)
         c2 = binding.slab_rebalance(table(own, rng.integers(0, 50, 4), rng.integers(0, 50, 4)), nz, c)
         assert np.all(np.abs(c2 - c) <= 1) and np.all(np.diff(c2) >= 6) and c2[0] == 0 and c2[-1] == nz
+        assert np.all(np.diff(c2) >= np.diff(c) - 1)
         c = c2
 
 
