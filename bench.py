@@ -156,27 +156,42 @@ def bind_to_gpu_numa_node(local):
         return None
 
 
-def cpu_oracle_run(scene, res, steps, warmup, threads=0):
-    """Times the CPU oracle (the reference's algorithm restated, oracle/) on this box's host cores."""
+def cpu_oracle_run(scene, res, steps, warmup, threads=0, budget_s=None):
+    """Times the CPU oracle (the reference's algorithm restated, oracle/) on this box's host cores.  With a time
+    budget the run stops early once it is spent (at least 2 timed substeps); returns the substeps actually timed."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_binding as ob
     p = ob.default_params(res, scene)
     pos = ob.scene(p)
     orc = ob.Oracle(p, pos, boundary_seed=0, threads=threads)
+    t_all = time.perf_counter()
     for _ in range(warmup):
         orc.advance()
+        if budget_s is not None and time.perf_counter() - t_all > 0.25 * budget_s:
+            break
     t0 = time.perf_counter()
+    done = 0
     for _ in range(steps):
         orc.advance()
+        done += 1
+        if budget_s is not None and done >= 2 and time.perf_counter() - t_all > budget_s:
+            break
     dt = time.perf_counter() - t0
     n = len(pos)
     orc.close()
-    return n * steps / dt, n, dt
+    return n * done / dt, n, dt, done
 
 
 def base_config(workload, scene, res, n_total, n_gpus):
     """Identical in both arms (--impl b200 / reference): what the workload IS.  How the GPU arm ran it (slab axis, ghost
     fraction, settle time ...) goes into the top-level `run` object."""
+    if n_total is None:  # the reference arm at N > 1 did not generate the large scene: count it through the C-ABI (host side only)
+        import simplefluid_b200 as sf
+        import ctypes as C
+        p = sf.default_params(res, scene)
+        cnt = C.c_uint64(0)
+        sf.library().sf_scene_generate(C.byref(p), sf.SCENES[scene], None, 0, C.byref(cnt))
+        n_total = cnt.value
     return {"workload": workload, "scene": scene, "resolution": res, "particles_total": int(n_total),
             "particles_per_gpu": int(n_total // n_gpus), "grid_cells": int(res) ** 3, "boundary_seed": 0,
             "parallelism": f"slab x{n_gpus} (one process per GPU)" if n_gpus > 1 else "single",
@@ -193,15 +208,24 @@ def run_reference(args):
     if rank != 0:
         return
     scene, res, scaling = workload_config(args.workload, args.gpus)
+    # The CPU arm runs on ONE host whatever N is.  At N = 1 it runs the GPU arm's very configuration; at N > 1 a weak-scaling
+    # workload would be N times larger (64 M particles at N = 8: 8 s per substep), so it runs the N = 1 size of the same
+    # workload and says so -- the metric is per particle-step and the CPU cost per particle does not fall with size.
+    cpu_res = res if scaling == "strong" else workload_config(args.workload, 1)[1]
     cores = len(os.sched_getaffinity(0)) or os.cpu_count() or 1
-    value, n, secs = cpu_oracle_run(scene, res, args.steps, args.warmup)
-    sample = (f"{scene} res {res} ({n} particles, the GPU arm's configuration at {args.gpus} GPU(s)) x {args.steps} substeps from the "
-              f"initial lattice, OpenMP {cores} threads, serial cell insertion as in the reference")
+    value, n, secs, done = cpu_oracle_run(scene, cpu_res, args.steps, args.warmup, budget_s=150.0)
+    sample = (f"{scene} res {cpu_res} ({n} particles" + (", the GPU arm's configuration" if cpu_res == res else
+              f", the N = 1 size of this workload; the GPU arm at {args.gpus} GPUs runs res {res}") +
+              f") x {done} substeps from the initial lattice, OpenMP {cores} threads, serial cell insertion as in the reference")
+    config = base_config(args.workload, scene, res, n if cpu_res == res else None, args.gpus)
+    if cpu_res != res:
+        config["reference_arm_resolution"] = cpu_res
+        config["reference_arm_particles"] = int(n)
     line = {
         "impl": "reference", "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True,
+        "steps": done, "warmup": args.warmup, "ms_per_step": secs / done * 1e3, "higher_is_better": True,
         "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": base_config(args.workload, scene, res, n, args.gpus),
+        "config": config,
         "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -393,16 +417,19 @@ def run_b200(args):
             traffic, traffic_src = tj.get(dom), tj.get("_source")
     except Exception:
         pass
-    ksum = sum(x[0] / x[1] for x in step_kernels.values())
-    kernel_share = {k: round(v[0] / v[1] / ksum, 4) for k, v in step_kernels.items()}
-    kernel_ms = {k: round(v[0] / v[1], 4) for k, v in step_kernels.items()}
+    # per SUBSTEP: a slab substep launches the force and integrate kernels twice (edge layers, interior layers) and
+    # k_begin_step twice, so totals are divided by the number of profiled substeps (= launches of the density pass)
+    nprof = max(int(step_kernels.get("k_density", (0.0, 1))[1]), 1)
+    ksum = sum(x[0] for x in step_kernels.values()) / nprof
+    kernel_share = {k: round(v[0] / nprof / ksum, 4) for k, v in step_kernels.items()}
+    kernel_ms = {k: round(v[0] / nprof, 4) for k, v in step_kernels.items()}
 
     # ---- CPU baseline on a bounded sample (rank 0, N = 1 only): same scene and resolution -----------
     cpu = None
     if n_gpus == 1 and not args.no_cpu_baseline:
         cores = len(os.sched_getaffinity(0)) or os.cpu_count() or 1
         csteps = max(2, min(80, int(12e6 * 12 / max(n_total, 1))))  # ~10-20 s of CPU work
-        cv, cn, secs = cpu_oracle_run(scene, res, csteps, 1)
+        cv, cn, secs, csteps = cpu_oracle_run(scene, res, csteps, 1, budget_s=40.0)
         cpu = {"value": cv, "unit": "particle-steps/s", "cores": cores, "kind": "port",
                "sample": f"{scene} res {res} ({cn} particles, same configuration) x {csteps} substeps from the initial lattice in {secs:.1f} s, OpenMP {cores} threads"}
 
