@@ -21,7 +21,8 @@ developed region.  `e2e` = the same metric through the host-buffer C-ABI calls (
 the timed region); `cpu_baseline` = the CPU oracle ("port": line-faithful transcription, the reference cannot be built
 -- BASELINE.md section 2) on this box's host cores on a bounded sample of the SAME scene and resolution; at N > 1
 `parity_vs_single_gpu` = the slab run gathered by particle id and compared bit for bit with a single-GPU run of the
-same substeps on rank 0.
+same substeps on rank 0; at N = 1 `parity_vs_reference_binary` = the first substeps of the run against the checksums of
+the reference binary's own outputs for the same scene (tests/golden/exe_fullsize_checksums.json).
 """
 import argparse
 import json
@@ -294,6 +295,28 @@ def verify_vs_single_gpu(sf, gpu, dist, rank, local, p, pos, total_steps):
     return flag[0]
 
 
+def verify_vs_reference_binary(gpu, scene, res):
+    """N = 1: the first substeps of this very run against the checksums of the REFERENCE BINARY's own outputs for the same
+    scene and resolution (tests/golden/exe_fullsize_checksums.json; tests/golden/make_exe_fullsize.py produced them by
+    executing Prebuild/SimpleFluid.exe's compiled step).  Returns (flag or None when no fixture covers the scene, substeps used)."""
+    import hashlib
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "exe_fullsize_checksums.json")) as f:
+            cases = json.load(f)["cases"]
+    except Exception:
+        return None, 0
+    rec = next((c for c in cases.values() if c["scene"] == scene and int(c["resolution"]) == int(res)), None)
+    if rec is None:
+        return None, 0
+    digest = lambda a: hashlib.sha256(memoryview(np.ascontiguousarray(a)).cast("B")).hexdigest()
+    ok = True
+    for k, want in enumerate(rec["steps"]):
+        ok = ok and float(np.float32(gpu.advanceFrame())) == float(np.float32(rec["dts"][k]))
+        got = {"cell": gpu.cellIndex(), "rho": gpu.density(), "x": gpu.getParticles(), "v": gpu.getVelocity()}
+        ok = ok and all(digest(got[f]) == want[f] for f in got)
+    return bool(ok), len(rec["steps"])
+
+
 def run_b200(args):
     import simplefluid_b200 as sf
 
@@ -320,8 +343,13 @@ def run_b200(args):
     gpu.makeReady()
     total_particles = float(n_total)
 
+    # ---- N = 1: the first substeps against the reference binary's own outputs (part of the warm-up) -------------
+    ref_parity, used = (None, 0)
+    if not multi and not args.no_verify:
+        ref_parity, used = verify_vs_reference_binary(gpu, scene, res)
+
     # ---- device-resident throughput: at rest, then on the developed flow ------------------------
-    gpu.advanceSteps(args.warmup)
+    gpu.advanceSteps(max(args.warmup - used, 0))
     gpu.synchronize()
     barrier(dist)
     ms_rest, _, _ = timed_region(gpu, dist, local, args.steps, profile=False)
@@ -462,6 +490,8 @@ def run_b200(args):
     }
     if multi:
         line["parity_vs_single_gpu"] = parity
+    else:
+        line["parity_vs_reference_binary"] = ref_parity  # null: no fixture for this scene / --no-verify
     print(json.dumps(line), flush=True)
     gpu.close()
 

@@ -52,6 +52,26 @@ def test_oracle_reproduces_the_reference_binarys_outputs(ob, name):
     orc.close()
 
 
+def test_oracle_matches_the_binary_at_full_size_c2(ob):
+    """BASELINE.json configs[1] at full size (CubeDrop, 1,000,000 particles), two substeps: SHA-256 of every field against
+    the checksums of the reference binary's own outputs (tests/golden/make_exe_fullsize.py).  The larger configurations
+    (8 M ... 64 M particles) are checked the same way on the GPU (tests/test_parity_gpu.py)."""
+    import hashlib
+    import json
+    rec = json.load(open(os.path.join(HERE, "golden", "exe_fullsize_checksums.json")))["cases"]["C2_cubedrop_1m"]
+    p = ob.default_params(rec["resolution"], rec["scene"])
+    pos = ob.scene(p)
+    assert len(pos) == rec["n"] == 1000000
+    orc = ob.Oracle(p, pos, boundary_seed=0)
+    digest = lambda a: hashlib.sha256(memoryview(np.ascontiguousarray(a)).cast("B")).hexdigest()
+    for k, want in enumerate(rec["steps"]):
+        assert np.float32(orc.advance()) == np.float32(rec["dts"][k])
+        got = {"cell": orc.cell_index(), "rho": orc.density(), "acc": orc.accel(), "x": orc.positions(), "v": orc.velocities()}
+        for f in want:
+            assert digest(got[f]) == want[f], f"{f} after substep {k}"
+    orc.close()
+
+
 # ---- live runs of the binary (build container only) ---------------------------------------------------------------
 def compare_live(ob, p, pos, vel, steps, seed):
     E = eh.run(p, pos, steps, seed=seed, vel=vel)

@@ -134,6 +134,40 @@ def test_cuda_path_reproduces_the_reference_binarys_outputs(sf, name):
     gpu.close()
 
 
+def _fullsize_cases():
+    import json
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "exe_fullsize_checksums.json")
+    return json.load(open(path))["cases"] if os.path.exists(path) else {}
+
+
+@pytest.mark.parametrize("name", sorted(_fullsize_cases()))
+def test_full_size_configs_match_the_reference_binary(sf, name):
+    """Every BASELINE.json configuration AT ITS FULL SIZE (C2 1 M, C3 8.03 M, the 8.09 M weak-scaling unit, C4 16.05 M,
+    C5 64.2 M particles on one GPU): dt and the SHA-256 of cell indices, density, acceleration, positions and velocities
+    after each substep equal those of the reference's own compiled step (tests/golden/make_exe_fullsize.py ran
+    Prebuild/SimpleFluid.exe's makeReady / advanceFrame on the same scenes; only the checksums travel)."""
+    import hashlib
+    rec = _fullsize_cases()[name]
+    p = sf.default_params(rec["resolution"], rec["scene"])
+    pos = sf.scene_generate(p)
+    assert len(pos) == rec["n"]
+    gpu = sf.SPHSolver(p)
+    gpu.setParticles(pos)
+    del pos
+    gpu.generateBoundaryParticles(0)
+    gpu.setCapture(True)
+    gpu.makeReady()
+    assert list(gpu.gridDims()) == rec["grid"]
+    digest = lambda a: hashlib.sha256(memoryview(np.ascontiguousarray(a)).cast("B")).hexdigest()
+    for k, want in enumerate(rec["steps"]):
+        assert np.float32(gpu.advanceFrame()) == np.float32(rec["dts"][k])
+        for field, get in (("cell", gpu.cellIndex), ("rho", gpu.density), ("acc", gpu.accel), ("x", gpu.getParticles), ("v", gpu.getVelocity)):
+            assert digest(get()) == want[field], f"{name}: {field} after substep {k} differs from the reference binary's output"
+    d = gpu.diagnostics()
+    assert d["fallback_bricks"] == 0 and d["particles_without_list"] == 0  # the production path, not the traversal fallback
+    gpu.close()
+
+
 def test_1000_substeps_dambreak_reference_default(sf, ob):
     """Positions after 1000 substeps (~1 s: the whole collapse-and-splash phase).  Stated tolerance: 0
     (bit-identical); the looser 1e-5*box gate is asserted first to size any regression."""
