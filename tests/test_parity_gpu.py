@@ -534,6 +534,34 @@ def test_production_list_capacity_overflow_falls_back(sf, ob):
     orc.close()
 
 
+@pytest.mark.parametrize("per_cell", [12, 18])
+def test_compressed_flow_bricks_are_processed_in_parts(sf, ob, per_cell):
+    """More particles per cell than a staging buffer holds for a whole 8x4x4-cell brick (3,584 halo particles = 10 per
+    cell): the brick is processed in halves (12 per cell) or single layers (18 per cell) with the list walkers following
+    the same split -- bit-identical to the oracle, production list included, and without the traversal fallback."""
+    rng = np.random.default_rng(per_cell)
+    p = sf.default_params(16, "CubeDrop")
+    h = p.kernelRadius
+    cells = np.array([14, 10, 10])
+    n = int(np.prod(cells)) * per_cell
+    lo = np.array([-1.0 + h, -1.0 + 3 * h, -1.0 + 3 * h])
+    pos = (rng.random((n, 3)) * (cells * h) + lo).astype(np.float32)
+    vel = (rng.standard_normal((n, 3)) * 0.05).astype(np.float32)
+    gpu, orc, _ = make_pair(sf, ob, "CubeDrop", 16, pos=pos, vel=vel)
+    inv_step = float(sf.binding.build_tables(p)[2][2])
+    for _ in range(2):
+        x0 = orc.positions()
+        ocnt, oids = orc.neighbors()
+        assert orc.advance() == gpu.advanceFrame()
+        check_step_fields(gpu, orc, ocnt, oids)
+        check_production_list(gpu, x0, ocnt, oids, inv_step)
+    d = gpu.diagnostics()
+    assert d["fallback_bricks"] == 0 and d["particles_without_list"] == int((ocnt > 96).sum())
+    assert d["nbr_mean"] > 2.0 * per_cell  # (particles whose list overflowed do not count)
+    gpu.close()
+    orc.close()
+
+
 def test_production_list_crowded(sf, ob):
     """Ragged, crowded cells (> 64 neighbours, coincident points): list order and table index 0 entries."""
     rng = np.random.default_rng(11)
