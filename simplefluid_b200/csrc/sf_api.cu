@@ -298,7 +298,9 @@ void fill_dev_params(sf_solver* s)
     P.n    = s->n;
     P.npad = s->npad;
     P.kmax = s->kmax;
-    P.listTiled = s->listTiled ? 1 : 0;
+    // the density pass addresses a list column with a 32-bit word offset k * stride: plain ELL (stride npad, a comparison
+    // variant) only while a column spans fewer than 2^32 words, else the tiled layout (stride 32)
+    P.listTiled = (s->listTiled || static_cast<unsigned long long>(s->npad) * static_cast<unsigned long long>(s->kmax) >= (1ull << 32)) ? 1 : 0;
     P.nbx  = (s->grid[0] + BX - 1) / BX;
     P.nby  = (s->nM() + BY - 1) / BY;
     P.nbz  = (s->nS() + BZ - 1) / BZ;
