@@ -6,7 +6,8 @@
 //   keys/vals[2]  : radix-sort ping-pong (cell key, slot in A)
 //   posB/velB/idB : state re-sorted by cell key for THIS substep.  The .w lanes carry the
 //                   per-particle terms the pair loops need so that every neighbour costs one
-//                   128-bit load:  posB.w = P(rho)/rho^2 (pressure term), velB.w = 1/rho
+//                   128-bit load:  posB.w = P(rho)/rho^2 (pressure term, written by the density pass together
+//                   with x, y, z as one 16-byte element), velB.w = 1/rho (written by the force pass with v*)
 //   keyB          : cell key per sorted slot ((cz*ny+cy)*nx+cx, reference A.7)
 //   cellTab       : uint2 {begin,end} sorted-slot range per cell, {0,0} when empty
 //   rho           : density per sorted slot

@@ -450,8 +450,8 @@ __global__ void k_reorder_pos(const uint32_t* __restrict__ keys, const uint32_t*
     idB[dst]           = myId;
 }
 
-// ... and the velocity gather straight from the uploaded xyz array (id = upload index) once it has arrived, keeping
-// velB.w = 1/rho of the density pass, fused with computeMaxVel (A.5) of the uploaded velocities
+// ... and the velocity gather straight from the uploaded xyz array (id = upload index) once it has arrived (the .w
+// lane is filled by the force pass), fused with computeMaxVel (A.5) of the uploaded velocities
 __global__ void k_gather_vel_host(const float* __restrict__ velXYZ, const uint32_t* __restrict__ idB, float4* __restrict__ velB,
                                   uint32_t n, DevState* st)
 {
@@ -461,7 +461,7 @@ __global__ void k_gather_vel_host(const float* __restrict__ velXYZ, const uint32
     if(p < n) {
         const size_t o = 3 * static_cast<size_t>(idB[p]);
         const float  vx = velXYZ[o], vy = velXYZ[o + 1], vz = velXYZ[o + 2];
-        velB[p]        = make_float4(vx, vy, vz, velB[p].w);
+        velB[p]        = make_float4(vx, vy, vz, 0.f);
         m              = fmaxf(m, (vy * vy + vx * vx) + vz * vz);
     }
     for(int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));

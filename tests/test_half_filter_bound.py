@@ -35,12 +35,13 @@ def filter_passes(xq, xp, centre, h):
     uq = (xq.astype(np.float64) * np.float64(invh) + off.astype(np.float64)).astype(F32).astype(F16)
     up = (xp.astype(np.float64) * np.float64(invh) + off.astype(np.float64)).astype(F32).astype(F16)
     d = uq - up  # HADD2, correctly rounded
-    d2 = d[:, 0] * d[:, 0]  # HMUL2
-    d2 = half_fma(d[:, 1], d[:, 1], d2)
-    d2 = half_fma(d[:, 2], d[:, 2], d2)
     radius2 = F32(h) * F32(h)
     thr = half_round_up(F32(F32(F32(radius2 * invh) * invh) * F32(1.0135)))
-    return d2 <= thr, thr
+    # t = ((thr - dx^2) - dy^2) - dz^2 as three half-precision fused multiply-adds; kept when the sign bit of t is clear
+    t = half_fma(-d[:, 0], d[:, 0], np.full(len(d), thr, dtype=F16))
+    t = half_fma(-d[:, 1], d[:, 1], t)
+    t = half_fma(-d[:, 2], d[:, 2], t)
+    return ~np.signbit(t), thr
 
 
 def exact_in_range(xq, xp, h):
@@ -104,42 +105,61 @@ def test_worst_case_corner_of_the_halo():
         assert near.sum() > 10_000 and np.all(passed[near])
 
 
-def test_hit_nibble_and_window_mask_assembly():
-    """PRMT + LOP3 + IMAD of filter_quads: four 0xffff / 0 half-masks -> bits 28..31, shifted in quad by quad."""
-    def nibble(ma, mb):
-        tq = (ma & 0xFF) | (((ma >> 16) & 0xFF) << 8) | ((mb & 0xFF) << 16) | (((mb >> 16) & 0xFF) << 24)  # __byte_perm(ma, mb, 0x6420)
-        return ((tq & 0x08040201) * 0x10101010) & 0xF0000000
+def test_miss_nibble_and_window_mask_assembly():
+    """prmt (sign-replicated bytes 1 and 3 of both registers) + LOP3 + IMAD of filter_quads: the sign bits of four
+    half-precision t values -> bits 28..31 (miss bits), shifted in quad by quad; the caller inverts them."""
+    def prmt_signs(ta, tb):
+        b = [(ta >> 8) & 0xFF, (ta >> 24) & 0xFF, (tb >> 8) & 0xFF, (tb >> 24) & 0xFF]
+        return sum((0xFF if x & 0x80 else 0) << (8 * i) for i, x in enumerate(b))
 
+    def nibble(ta, tb):
+        return ((prmt_signs(ta, tb) & 0x08040201) * 0x10101010) & 0xF0000000
+
+    rng = np.random.default_rng(0)
     for bits in range(16):
-        ma = (0xFFFF if bits & 1 else 0) | (0xFFFF0000 if bits & 2 else 0)
-        mb = (0xFFFF if bits & 4 else 0) | (0xFFFF0000 if bits & 8 else 0)
-        assert nibble(ma, mb) >> 28 == bits
-    rng = np.random.default_rng(1)
+        for _ in range(20):
+            junk = [int(rng.integers(0, 0x8000)) for _ in range(4)]  # any magnitude bits
+            h = [junk[i] | (0x8000 if bits >> i & 1 else 0) for i in range(4)]
+            assert nibble(h[0] | h[1] << 16, h[2] | h[3] << 16) >> 28 == bits
     for nq in range(1, 9):
         for _ in range(50):
-            hits = rng.integers(0, 2, size=4 * nq)
+            miss = rng.integers(0, 2, size=4 * nq)
             mask = 0
             for q in range(nq):
-                b = hits[4 * q:4 * q + 4]
-                ma = (0xFFFF if b[0] else 0) | (0xFFFF0000 if b[1] else 0)
-                mb = (0xFFFF if b[2] else 0) | (0xFFFF0000 if b[3] else 0)
-                mask = ((mask >> 4) | nibble(ma, mb)) & 0xFFFFFFFF
+                b = [0x8000 if v else 0x3c00 for v in miss[4 * q:4 * q + 4]]
+                mask = ((mask >> 4) | nibble(b[0] | b[1] << 16, b[2] | b[3] << 16)) & 0xFFFFFFFF
             mask >>= 4 * (8 - nq)
-            assert mask == sum(int(v) << i for i, v in enumerate(hits))
+            assert mask == sum(int(v) << i for i, v in enumerate(miss))
 
 
-def test_window_range_mask():
-    """Bits of a 32-slot window that belong to the lane's own run [pre, pre + len) of the aligned window, per chunk."""
-    def range_mask(pre, length, q0):
-        lo = pre - 4 * q0
-        hi = lo + length
-        mhi = 0xFFFFFFFF if hi >= 32 else (0 if hi <= 0 else (1 << hi) - 1)
-        mlo = 0xFFFFFFFF if lo <= 0 else (0 if lo >= 32 else ~((1 << lo) - 1) & 0xFFFFFFFF)
-        return mhi & mlo
+def test_window_mask_of_the_pooled_exact_phase():
+    """The hit mask of one 32-slot window as k_density_brick assembles it: miss bits of the quads read from the
+    quad-aligned start a0 + c0 (lo: 8 quads, hi: the ninth), funnel-shifted by pre = jbase - a0, inverted, restricted
+    to the lane's own run [0, len - c0) and cleared at the particle's own slot; shifts clamp at 32 (PTX shl)."""
+    def shl_clamp(a, n):
+        return (a << n) & 0xFFFFFFFF if 0 <= n < 32 else 0
 
-    for pre in range(4):
-        for length in (0, 1, 5, 29, 32, 33, 61, 64, 100):
-            nq = (pre + length + 3) // 4 if length else 0
-            for q0 in range(0, max(nq, 1) + 8, 8):
-                want = sum(1 << i for i in range(32) if pre <= 4 * q0 + i < pre + length)
-                assert range_mask(pre, length, q0) == want
+    rng = np.random.default_rng(3)
+    for _ in range(4000):
+        jbase = int(rng.integers(0, 3000))
+        length = int(rng.choice([0, 1, 3, 17, 24, 31, 32, 33, 40, 56, 57, 63, 64, 90]))
+        maxend = max((jbase & 3) + length, int(rng.integers(0, 100)))  # some other lane may need more quads
+        self_slot = jbase + int(rng.integers(-5, length + 5))
+        hits = rng.integers(0, 2, size=jbase + 200)  # filter verdict per halo slot
+        a0, pre = jbase & ~3, jbase & 3
+        c0 = 0
+        while c0 < max(length, 1) and length:
+            quads = (min(maxend - c0, 35) + 3) >> 2
+            assert 1 <= quads <= 9
+            nq_lo = min(quads, 8)
+            lo = sum((1 - int(hits[a0 + c0 + i])) << i for i in range(4 * nq_lo))            # after lo >>= 4 * (8 - nqLo)
+            hi = sum((1 - int(hits[a0 + c0 + 32 + i])) << i for i in range(4)) if quads > 8 else 0
+            mask = ~(((hi << 32 | lo) >> pre) & 0xFFFFFFFF) & 0xFFFFFFFF
+            vlen = max(length - c0, 0)
+            mask &= ~shl_clamp(0xFFFFFFFF, vlen) & 0xFFFFFFFF
+            ts = (self_slot - (jbase + c0)) & 0xFFFFFFFF
+            mask &= ~shl_clamp(1, ts if ts < 2**31 else 99) & 0xFFFFFFFF
+            want = sum(1 << i for i in range(32)
+                       if c0 + i < length and hits[jbase + c0 + i] and jbase + c0 + i != self_slot)
+            assert mask == want, (jbase, length, maxend, c0)
+            c0 += 32
