@@ -177,9 +177,11 @@ int sf_grid_dims(sf_solver* s, int32_t n3[3]);                     /* Grid3D::se
  * counts, particles without a list, particles resident on this rank}.  Synchronises. */
 int sf_diagnostics(sf_solver* s, uint64_t out[8]);
 
-/* Development counters of instrumented builds (make EXTRA=-DSF_EXP_WAITSTAT): warp cycles of the density pass spent
- * waiting for a staged brick, (unused), in the exact phase, in total; cumulative.  Zeros in a normal build. */
-int sf_debug_counters(sf_solver* s, uint64_t out[4]);
+/* Development counters of instrumented builds (make EXTRA=-DSF_EXP_WAITSTAT), density pass, cumulative: consumer-warp
+ * cycles waiting for a staged brick, refills counted, consumer cycles in the exact phase, consumer cycles in total,
+ * producer cycles per refill (buffer free -> brick released), of which waiting for the TMA copies, of which converting,
+ * (unused).  Zeros in a normal build. */
+int sf_debug_counters(sf_solver* s, uint64_t out[8]);
 
 /* ---- measurement ---------------------------------------------------------------------------- */
 /* Per-kernel CUDA-event timing on the launching stream.  sf_profile_enable(s, N): every N-th substep is timed

@@ -394,7 +394,7 @@ class SPHSolver:
         self._ck(self.L.sf_set_list_capacity(self.h, int(kmax)))
 
     def debugCounters(self):
-        out = (C.c_uint64 * 4)()
+        out = (C.c_uint64 * 8)()
         self._ck(self.L.sf_debug_counters(self.h, out))
         return [int(x) for x in out]
 

@@ -1297,7 +1297,7 @@ int sf_host_free(void* p)
     return SF_OK;
 }
 
-int sf_debug_counters(sf_solver* s, uint64_t out[4])
+int sf_debug_counters(sf_solver* s, uint64_t out[8])
 {
     int rc = require_ready(s);
     if(rc) return rc;
@@ -1305,7 +1305,7 @@ int sf_debug_counters(sf_solver* s, uint64_t out[4])
     SF_CUDA(s, cudaSetDevice(s->device));
     rc = read_state(s);
     if(rc) return rc;
-    for(int i = 0; i < 4; ++i) out[i] = s->hostState->dbg[i];
+    for(int i = 0; i < 8; ++i) out[i] = s->hostState->dbg[i];
     return SF_OK;
 }
 

@@ -70,7 +70,10 @@ struct DevState {
     unsigned brickCount;  // non-empty bricks of this substep
     unsigned cursor[6];   // work cursors of the persistent pair kernels (density, force, viscosity edge / interior, Shepard)
     unsigned fallbackBricks, fallbackParticles; // diagnostics: halos that did not fit smem / lists that overflowed
-    unsigned long long dbg[4]; // SF_EXP_WAITSTAT builds: warp cycles of the density pass spent waiting for a brick / filtering / in the exact phase / total
+    // SF_EXP_WAITSTAT builds, density pass: consumer-warp cycles waiting for a brick / refills counted / consumer cycles in
+    // the exact phase / consumer cycles in total / producer cycles from "buffer free" to "brick released" (refill latency),
+    // of which waiting for the TMA copies / converting to half precision / (unused)
+    unsigned long long dbg[8];
 };
 
 enum : unsigned { SF_DEVERR_NBR_OVERFLOW = 1u, SF_DEVERR_WALL_OVERFLOW = 2u, SF_DEVERR_DOMAIN = 4u };
