@@ -68,7 +68,6 @@ struct sf_solver {
     DevState*    hostState = nullptr; // pinned
     uint32_t     radixBlocks = 0;
     // Kernel variants, all bit-identical (tools/variant_bench.py); the environment overrides exist for A/B timing:
-    bool         listTiled = true;       // SF_LIST=tiled (default): [slot/32][k][slot%32]; ell: [k][slot]
     bool         countSort = true;       // SF_SORT=count (default): counting sort by cell; radix: three LSD radix passes
     uint32_t*    cellTileSums = nullptr; // counting sort: per-tile particle counts of the cell table
     uint64_t     cellTileCap = 0;
@@ -298,9 +297,6 @@ void fill_dev_params(sf_solver* s)
     P.n    = s->n;
     P.npad = s->npad;
     P.kmax = s->kmax;
-    // the density pass addresses a list column with a 32-bit word offset k * stride: plain ELL (stride npad, a comparison
-    // variant) only while a column spans fewer than 2^32 words, else the tiled layout (stride 32)
-    P.listTiled = (s->listTiled || static_cast<unsigned long long>(s->npad) * static_cast<unsigned long long>(s->kmax) >= (1ull << 32)) ? 1 : 0;
     P.nbx  = (s->grid[0] + BX - 1) / BX;
     P.nby  = (s->nM() + BY - 1) / BY;
     P.nbz  = (s->nS() + BZ - 1) / BZ;
@@ -842,7 +838,6 @@ int sf_create(const sf_params* p, int device, sf_solver** out)
     }
     s->stream = s->ownStream;
     s->useGraph = std::getenv("SF_NO_GRAPH") == nullptr;
-    if(const char* m = std::getenv("SF_LIST")) s->listTiled = std::strcmp(m, "ell") != 0;
     if(const char* m = std::getenv("SF_SORT")) s->countSort = std::strcmp(m, "radix") != 0;
     if(const char* m = std::getenv("SF_KMAX")) s->kmax = std::min(std::max(std::atoi(m), 8), 16383);
     s->occDensity = std::max(s->occDensity, 1);

@@ -52,7 +52,6 @@ struct DevParams {
     // cell counts and every "z"/"layer" of the slab logic means the slow axis.  The 3x3 rows of a neighbourhood
     // are always visited in the reference's order (dz outer, dy inner).
     int      axisS;
-    int      listTiled;   // neighbour-list layout: 1 = [slot/32][k][slot%32] (default), 0 = ELL [k][slot]
     uint32_t nbnd[6];     // wall particle counts
     uint32_t bndStride;   // slots per wall in the bnd array
 };

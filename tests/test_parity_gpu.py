@@ -342,10 +342,10 @@ def test_crowded_cells_collisions(sf, ob):
     orc.close()
 
 
-@pytest.mark.parametrize("env", [dict(SF_SORT="radix"), dict(SF_LIST="ell"), dict(SF_SORT="radix", SF_LIST="ell")])
+@pytest.mark.parametrize("env", [dict(SF_SORT="radix")])
 def test_kernel_variants_bit_identical(sf, ob, monkeypatch, env):
-    """The selectable kernel variants (radix passes instead of the counting sort, ELL instead of the tiled neighbour
-    list; read at sf_create) give the oracle's bits too."""
+    """The selectable kernel variant (radix passes instead of the counting sort; read at sf_create) gives the oracle's
+    bits too."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     gpu, orc, _ = make_pair(sf, ob, "DoubleDambreak", 40)

@@ -1,7 +1,7 @@
-"""Compare the selectable kernel variants (SF_SORT=radix|count, SF_LIST=tiled|ell) on one GPU: bit-equality of
+"""Compare the selectable kernel variants (SF_SORT=radix|count) on one GPU: bit-equality of
 the state after `steps` substeps against the first variant, per-kernel times, and the host-buffer step.
 Development aid; usage:  python tools/variant_bench.py [res] [steps] [variant ...]  where a variant is
-sort+list, e.g. count+tiled (the default), radix+tiled, count+ell."""
+the sort, count (the default) or radix."""
 import os
 import sys
 import time
@@ -14,9 +14,7 @@ import simplefluid_b200 as sf  # noqa: E402
 
 
 def make(scene, res, variant):
-    parts = variant.split("+")
-    os.environ["SF_SORT"] = parts[0]
-    os.environ["SF_LIST"] = parts[1] if len(parts) > 1 else "tiled"
+    os.environ["SF_SORT"] = variant.split("+")[0]
     p = sf.default_params(res, scene)
     pos = sf.scene_generate(p)
     gpu = sf.SPHSolver(p)  # the variant is read at sf_create
@@ -83,6 +81,6 @@ def e2e(scene, res, steps, variant):
 if __name__ == "__main__":
     res = int(sys.argv[1]) if len(sys.argv) > 1 else 203
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
-    variants = sys.argv[3:] or ["count+tiled", "radix+tiled", "count+ell"]
+    variants = sys.argv[3:] or ["count", "radix"]
     run("Dambreak", res, steps, variants)
     e2e("Dambreak", res, 10, variants[0])
