@@ -75,8 +75,11 @@ struct sf_solver {
     int          occDensity = 1, occForce = 1, occVisc = 1;
     uint32_t     numBricks = 0, brickCap = 0;
     uint32_t     nSlots = 0; // live + dead slots of the A arrays (== n on a single GPU)
-    cudaGraphExec_t stepGraph = nullptr; // captured substep (single GPU); dropped whenever the launch arguments change
-    uint64_t        graphLaunches = 0;
+    // captured substep (single GPU); dropped whenever the launch arguments change.  [1]: the steady form, whose cell
+    // counts were left by the previous substep's integrate kernel; [0]: with k_hash_count up front
+    cudaGraphExec_t stepGraph[2] = { nullptr, nullptr };
+    bool            hashed = false;      // cellCnt / keys[0] / vals[0] hold the binning of the current posA (written by k_visc_brick<true>)
+    uint64_t        graphLaunches[2] = { 0, 0 };
     bool            useGraph = true;
     int          axisS = 2;  // slow axis of the cell key: 2 = z (reference order), 1 = y (slab runs that are longer in y)
     int32_t      nS() const { return grid[axisS]; }
@@ -131,10 +134,19 @@ namespace
 {
 void drop_graph(sf_solver* s)
 {
-    if(s->stepGraph) {
-        cudaGraphExecDestroy(s->stepGraph);
-        s->stepGraph = nullptr;
+    for(cudaGraphExec_t& g : s->stepGraph) {
+        if(g) cudaGraphExecDestroy(g);
+        g = nullptr;
     }
+}
+
+// posA is about to change behind the integrate kernel's back (or the grid is): forget the fused binning
+int invalidate_binning(sf_solver* s)
+{
+    cudaError_t e = cudaSuccess;
+    if(s->hashed && s->B.cellCnt) e = cudaMemsetAsync(s->B.cellCnt, 0, sizeof(uint32_t) * s->ncells, s->stream);
+    s->hashed = false;
+    return e == cudaSuccess ? SF_OK : SF_ERR_CUDA;
 }
 
 void tl_mark(sf_solver* s, int mark, cudaStream_t st)
@@ -393,24 +405,21 @@ int enqueue_substep_launches(sf_solver* s, const float* velHostXYZ = nullptr)
         return SF_OK;
     }
     int cur = 0;
+    // single GPU, device-resident state: the integrate kernel also bins the new positions for the next substep
+    const bool fuseHash = s->countSort && !slab && !velHostXYZ;
     if(s->countSort) {
         // counting sort by cell (sf_kernels.cuh, section 1'): cell table first, then the slot permutation
-        {
-            LaunchScope  ls(s, K_CLEAR_CELLS);
-            const size_t nvec = (s->ncells * sizeof(uint2) + 15) / 16;
-            k_clear_cells<<<std::min<uint32_t>(cdiv(nvec, 256), s->numSMs * 16), 256, 0, st>>>(reinterpret_cast<uint4*>(B.cellTab), nvec, B.state);
-        }
         const uint32_t nc = static_cast<uint32_t>(s->ncells), ntiles = cdiv(nc, CS_TILE);
-        if(nSlots) {
+        if(nSlots && !(fuseHash && s->hashed)) {
             LaunchScope ls(s, K_HASH_COUNT);
-            k_hash_count<<<cdiv(nSlots, 256), 256, 0, st>>>(B.posA, B.idA, B.keys[0], B.vals[0], nSlots, P, B.cellTab, B.state);
+            k_hash_count<<<cdiv(nSlots, 256), 256, 0, st>>>(B.posA, B.idA, B.keys[0], B.vals[0], nSlots, P, B.cellCnt, B.state);
         }
         {
             LaunchScope ls(s, K_CELL_SCAN);
             s->launches += 2; // three kernels under one timing scope
-            k_cell_scan_reduce<<<ntiles, CS_THREADS, 0, st>>>(B.cellTab, nc, s->cellTileSums, B.state);
+            k_cell_scan_reduce<<<ntiles, CS_THREADS, 0, st>>>(B.cellCnt, nc, s->cellTileSums, B.state);
             k_radix_scan<<<1, 1024, 0, st>>>(s->cellTileSums, ntiles, B.radixTotals, B.state);
-            k_cell_scan_apply<<<ntiles, CS_THREADS, 0, st>>>(B.cellTab, nc, s->cellTileSums, B.brickFlag, P, B.state);
+            k_cell_scan_apply<<<ntiles, CS_THREADS, 0, st>>>(B.cellTab, B.cellCnt, nc, s->cellTileSums, B.brickFlag, P, B.state);
         }
         if(nSlots) {
             LaunchScope ls(s, K_COUNT_SCATTER);
@@ -500,8 +509,10 @@ int enqueue_substep_launches(sf_solver* s, const float* velHostXYZ = nullptr)
     if(slab) tl_mark(s, 4, st);
     if(!slab) {
         LaunchScope ls(s, K_VISC_INTEGRATE);
-        k_visc_brick<<<std::min<uint32_t>(pairGrid, s->numSMs * s->occVisc), kBrickThreads, kSmemPair, st>>>(B, P, 0);
+        if(fuseHash) k_visc_brick<true><<<std::min<uint32_t>(pairGrid, s->numSMs * s->occVisc), kBrickThreads, kSmemPair, st>>>(B, P, 0);
+        else k_visc_brick<false><<<std::min<uint32_t>(pairGrid, s->numSMs * s->occVisc), kBrickThreads, kSmemPair, st>>>(B, P, 0);
         SF_CUDA(s, cudaGetLastError());
+        s->hashed = fuseHash && n != 0;
         return SF_OK;
     }
     return slab_exchange(s, n, nSlots);
@@ -515,7 +526,8 @@ int enqueue_substep(sf_solver* s)
     // sampled per-kernel timing: the timed substeps use direct launches with events, the others the graph
     s->profiling = s->profEvery && (s->profCount++ % s->profEvery) == 0;
     if(s->slab.on || s->profiling || !s->useGraph || s->n == 0) return enqueue_substep_launches(s);
-    if(!s->stepGraph) {
+    const int gi = s->hashed ? 1 : 0; // the launch sequence depends on whether the previous substep left the binning
+    if(!s->stepGraph[gi]) {
         const uint64_t before = s->launches;
         cudaGraph_t    graph  = nullptr;
         SF_CUDA(s, cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
@@ -526,14 +538,15 @@ int enqueue_substep(sf_solver* s)
             return rc;
         }
         SF_CUDA(s, e);
-        e = cudaGraphInstantiate(&s->stepGraph, graph, 0);
+        e = cudaGraphInstantiate(&s->stepGraph[gi], graph, 0);
         cudaGraphDestroy(graph);
         SF_CUDA(s, e);
-        s->graphLaunches = s->launches - before;
-        s->launches      = before;
+        s->graphLaunches[gi] = s->launches - before;
+        s->launches          = before;
     }
-    SF_CUDA(s, cudaGraphLaunch(s->stepGraph, s->stream));
-    s->launches += s->graphLaunches;
+    SF_CUDA(s, cudaGraphLaunch(s->stepGraph[gi], s->stream));
+    s->launches += s->graphLaunches[gi];
+    s->hashed = s->countSort && s->n != 0; // what enqueue_substep_launches recorded while capturing
     return SF_OK;
 }
 
@@ -637,7 +650,7 @@ int slab_exchange(sf_solver* s, uint32_t n, uint32_t nSlots)
     if(extent) k_fill_u32<<<std::min<uint32_t>(cdiv(extent, 256), s->numSMs * 8), 256, 0, cs>>>(B.idA, extent, kInvalidId);
     if(n) {
         LaunchScope ls(s, K_VISC_INTEGRATE);
-        k_visc_brick<<<std::min<uint32_t>(pairGrid, s->numSMs * s->occVisc), kBrickThreads, kSmemPair, cs>>>(B, P, 1);
+        k_visc_brick<false><<<std::min<uint32_t>(pairGrid, s->numSMs * s->occVisc), kBrickThreads, kSmemPair, cs>>>(B, P, 1);
     }
     SF_CUDA(s, cudaEventRecord(L.evEdge, cs));
     tl_mark(s, 5, cs);
@@ -650,7 +663,7 @@ int slab_exchange(sf_solver* s, uint32_t n, uint32_t nSlots)
         }
         LaunchScope    ls(s, K_VISC_INTEGRATE);
         const uint32_t g = std::min<uint32_t>(pairGrid, s->numSMs * s->occVisc);
-        k_visc_brick<<<g > 32 ? g - std::min<uint32_t>(freeSlots, g - 1) : g, kBrickThreads, kSmemPair, cs>>>(B, P, 2);
+        k_visc_brick<false><<<g > 32 ? g - std::min<uint32_t>(freeSlots, g - 1) : g, kBrickThreads, kSmemPair, cs>>>(B, P, 2);
     }
     SF_CUDA(s, cudaEventRecord(L.evInterior, cs));
     tl_mark(s, 6, cs);
@@ -826,11 +839,12 @@ int sf_create(const sf_params* p, int device, sf_solver** out)
     if(e == cudaSuccess) e = cudaEventCreate(&s->timerB);
     if(e == cudaSuccess) e = cudaFuncSetAttribute(k_density_brick, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemDensity));
     if(e == cudaSuccess) e = cudaFuncSetAttribute(k_force_brick, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemPair));
-    if(e == cudaSuccess) e = cudaFuncSetAttribute(k_visc_brick, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemPair));
+    if(e == cudaSuccess) e = cudaFuncSetAttribute(k_visc_brick<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemPair));
+    if(e == cudaSuccess) e = cudaFuncSetAttribute(k_visc_brick<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemPair));
     if(e == cudaSuccess) e = cudaFuncSetAttribute(k_shepard_brick, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemPair));
     if(e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->occDensity, k_density_brick, kBrickThreads, kSmemDensity);
     if(e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->occForce, k_force_brick, kBrickThreads, kSmemPair);
-    if(e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->occVisc, k_visc_brick, kBrickThreads, kSmemPair);
+    if(e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->occVisc, k_visc_brick<true>, kBrickThreads, kSmemPair);
     if(e != cudaSuccess) {
         const std::string msg = std::string("sf_create: ") + cudaGetErrorString(e);
         sf_destroy(s);
@@ -858,7 +872,7 @@ void sf_destroy(sf_solver* s)
     DevBuffers& B = s->B;
     cudaFree(B.posA); cudaFree(B.velA); cudaFree(B.posB); cudaFree(B.velB); cudaFree(B.idA); cudaFree(B.idB);
     for(int i = 0; i < 2; ++i) { cudaFree(B.keys[i]); cudaFree(B.vals[i]); }
-    cudaFree(B.cellTab); cudaFree(B.rho); cudaFree(B.rho2); cudaFree(B.accel); cudaFree(B.nbrL); cudaFree(B.nbrCnt); cudaFree(B.brickFlag); cudaFree(B.brickList);
+    cudaFree(B.cellTab); cudaFree(B.cellCnt); cudaFree(B.rho); cudaFree(B.rho2); cudaFree(B.accel); cudaFree(B.nbrL); cudaFree(B.nbrCnt); cudaFree(B.brickFlag); cudaFree(B.brickList);
     cudaFree(B.tabW); cudaFree(B.tabG); cudaFree(B.bnd); cudaFree(B.radixCounts); cudaFree(B.radixTotals); cudaFree(B.state);
     cudaFree(s->stage);
     cudaFree(s->cellTileSums);
@@ -1040,8 +1054,11 @@ int sf_make_ready(sf_solver* s)
     }
     if(s->ncells > s->cellCap || !s->B.cellTab) {
         SF_CUDA(s, dev_alloc(s->B.cellTab, s->ncells + 2));
+        SF_CUDA(s, dev_alloc(s->B.cellCnt, s->ncells + 2));
         s->cellCap = s->ncells;
     }
+    SF_CUDA(s, cudaMemsetAsync(s->B.cellCnt, 0, sizeof(uint32_t) * (s->ncells + 2), s->stream)); // the counting sort expects zeros
+    s->hashed = false;
     if(s->countSort && (s->ncells > s->cellTileCap || !s->cellTileSums)) {
         SF_CUDA(s, dev_alloc(s->cellTileSums, static_cast<size_t>(cdiv(s->ncells, CS_TILE)) + 1));
         s->cellTileCap = s->ncells;
@@ -1205,7 +1222,8 @@ int sf_step_host(sf_solver* s, float* pos_xyz, float* vel_xyz, uint32_t n, float
     if(!s || !pos_xyz || !vel_xyz) return SF_ERR_INVALID;
     if(s->slab.on) return fail(s, SF_ERR_INVALID, "slab mode: use sf_upload_local / sf_advance_frame / sf_download_local");
     const bool sameShape = s->uploaded && s->ready && n == s->n && n > 0;
-    int        rc;
+    int        rc = invalidate_binning(s); // the positions come from the host
+    if(rc) return rc;
     if(!sameShape) {
         rc = sf_upload_particles(s, pos_xyz, vel_xyz, n);
         if(rc) return rc;
@@ -2162,6 +2180,8 @@ int sf_upload_local(sf_solver* s, const float* pos4, const float* vel4, const ui
     SF_CUDA(s, cudaSetDevice(s->device));
     const uint32_t m = s->slab.on ? s->nSlots : s->n;
     if(n != m) return fail(s, SF_ERR_INVALID, "sf_upload_local: slot count must match the resident state");
+    const int rc = invalidate_binning(s);
+    if(rc) return rc;
     SF_CUDA(s, cudaMemcpyAsync(s->B.posA, pos4, sizeof(float4) * m, cudaMemcpyHostToDevice, s->stream));
     SF_CUDA(s, cudaMemcpyAsync(s->B.velA, vel4, sizeof(float4) * m, cudaMemcpyHostToDevice, s->stream));
     SF_CUDA(s, cudaMemcpyAsync(s->B.idA, ids, sizeof(uint32_t) * m, cudaMemcpyHostToDevice, s->stream));

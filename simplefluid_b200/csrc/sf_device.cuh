@@ -10,6 +10,8 @@
 //                   with x, y, z as one 16-byte element), velB.w = 1/rho (written by the force pass with v*)
 //   keyB          : cell key per sorted slot ((cz*ny+cy)*nx+cx, reference A.7)
 //   cellTab       : uint2 {begin,end} sorted-slot range per cell, {0,0} when empty
+//   cellCnt       : particles per cell, counted for the next binning (by k_hash_count, or by k_visc_brick as it writes
+//                   the new positions); the scan that turns it into cellTab zeroes it again
 //   rho           : density per sorted slot
 //   brickList     : ids of the non-empty cell bricks (BX x BY x BZ cells) of this substep, in z-major
 //                   order; the three pair kernels are persistent CTAs that pull bricks from it
@@ -83,6 +85,7 @@ struct DevBuffers {
     uint32_t *keys[2], *vals[2];
     uint32_t *keyB;       // aliases the sorted keys buffer
     uint2*    cellTab;
+    uint32_t* cellCnt;    // counting sort: particles per cell of the NEXT binning; all zero between a scan and the next count
     float*    rho;
     float*    rho2;       // correctDensity scratch
     float4*   accel;      // capture only

@@ -291,35 +291,47 @@ k_radix_scatter(const uint32_t* __restrict__ keysIn, const uint32_t* __restrict_
 // (1') counting sort by cell key -- the alternative to the radix passes (SF_SORT=count).  A cell key has up to 27
 //      bits but only ~8 particles share one, and k_reorder re-ranks every cell by original id anyway, so the order
 //      in which particles arrive inside a cell is irrelevant:
-//        k_clear_cells -> k_hash_count (key + arrival rank in its cell, warp-aggregated atomics on cellTab[key].y)
-//        -> k_cell_scan_reduce / k_radix_scan (tile sums) / k_cell_scan_apply (cellTab = {begin,end}, brick flags)
+//        k_hash_count (key + arrival rank in its cell, warp-aggregated atomics on cellCnt[key])
+//        -> k_cell_scan_reduce / k_radix_scan (tile sums) / k_cell_scan_apply (cellTab = {begin,end}, brick flags;
+//           cellCnt zeroed for the next count)
 //        -> k_count_scatter (slot permutation in key order)
 //      One pass over the particles and one over the cells instead of three passes of (histogram, scan, scatter).
+//      On a single GPU with device-resident state the first step is fused into the previous substep's integrate
+//      kernel (k_visc_brick counts the cell of every new position as it writes it: count_into_cell below), so a
+//      substep starts at the scan.
 constexpr int CS_THREADS = 256;
 constexpr int CS_ITEMS   = 8;
 constexpr int CS_TILE    = CS_THREADS * CS_ITEMS;
 
-__global__ void k_hash_count(const float4* __restrict__ pos, const uint32_t* __restrict__ id, uint32_t* __restrict__ keys,
-                             uint32_t* __restrict__ ranks, uint32_t nSlots, DevParams P, uint2* __restrict__ cellTab, const DevState* st)
+// arrival rank of a particle in cell `key` (0xffffffff: not a live particle), one atomic per distinct key of the warp;
+// called by all 32 lanes
+__device__ __forceinline__ uint32_t count_into_cell(uint32_t* __restrict__ cellCnt, uint32_t key, bool live)
 {
-    if(st->skip) return;
-    const uint32_t i    = blockIdx.x * blockDim.x + threadIdx.x; // blockDim.x is a multiple of 32: whole warps reach the match
-    const int      lane = threadIdx.x & 31;
-    const bool     live = i < nSlots && id[i] != kInvalidId;
-    const uint32_t key  = live ? cell_key(P, pos[i]) : 0xffffffffu;
+    const int      lane   = threadIdx.x & 31;
     const uint32_t peers  = __match_any_sync(0xffffffffu, key);
     const int      leader = __ffs(peers) - 1;
     uint32_t       base   = 0u;
-    if(live && lane == leader) base = atomicAdd(&cellTab[key].y, static_cast<uint32_t>(__popc(peers)));
+    if(live && lane == leader) base = atomicAdd(&cellCnt[key], static_cast<uint32_t>(__popc(peers)));
     base = __shfl_sync(0xffffffffu, base, leader);
+    return base + __popc(peers & ((1u << lane) - 1u));
+}
+
+__global__ void k_hash_count(const float4* __restrict__ pos, const uint32_t* __restrict__ id, uint32_t* __restrict__ keys,
+                             uint32_t* __restrict__ ranks, uint32_t nSlots, DevParams P, uint32_t* __restrict__ cellCnt, const DevState* st)
+{
+    if(st->skip) return;
+    const uint32_t i    = blockIdx.x * blockDim.x + threadIdx.x; // blockDim.x is a multiple of 32: whole warps reach the match
+    const bool     live = i < nSlots && id[i] != kInvalidId;
+    const uint32_t key  = live ? cell_key(P, pos[i]) : 0xffffffffu;
+    const uint32_t rank = count_into_cell(cellCnt, key, live);
     if(i < nSlots) {
         keys[i]  = key;
-        ranks[i] = base + __popc(peers & ((1u << lane) - 1u));
+        ranks[i] = rank;
     }
 }
 
 __global__ void __launch_bounds__(CS_THREADS)
-k_cell_scan_reduce(const uint2* __restrict__ cellTab, uint32_t ncells, uint32_t* __restrict__ tileSums, const DevState* st)
+k_cell_scan_reduce(const uint32_t* __restrict__ cellCnt, uint32_t ncells, uint32_t* __restrict__ tileSums, const DevState* st)
 {
     if(st->skip) return;
     __shared__ uint32_t warpSum[CS_THREADS / 32];
@@ -327,7 +339,7 @@ k_cell_scan_reduce(const uint2* __restrict__ cellTab, uint32_t ncells, uint32_t*
     uint32_t       sum  = 0u;
 #pragma unroll
     for(int r = 0; r < CS_ITEMS; ++r)
-        if(base + r < ncells) sum += cellTab[base + r].y;
+        if(base + r < ncells) sum += cellCnt[base + r];
     for(int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     if((threadIdx.x & 31) == 0) warpSum[threadIdx.x >> 5] = sum;
     __syncthreads();
@@ -340,8 +352,8 @@ k_cell_scan_reduce(const uint2* __restrict__ cellTab, uint32_t ncells, uint32_t*
 
 // tileSums have been exclusive-scanned in place (k_radix_scan with one row)
 __global__ void __launch_bounds__(CS_THREADS)
-k_cell_scan_apply(uint2* __restrict__ cellTab, uint32_t ncells, const uint32_t* __restrict__ tileSums, uint32_t* __restrict__ brickFlag,
-                  DevParams P, const DevState* st)
+k_cell_scan_apply(uint2* __restrict__ cellTab, uint32_t* __restrict__ cellCnt, uint32_t ncells, const uint32_t* __restrict__ tileSums,
+                  uint32_t* __restrict__ brickFlag, DevParams P, const DevState* st)
 {
     if(st->skip) return;
     __shared__ uint32_t warpSum[CS_THREADS / 32];
@@ -351,7 +363,7 @@ k_cell_scan_apply(uint2* __restrict__ cellTab, uint32_t ncells, const uint32_t* 
     uint32_t       sum = 0u;
 #pragma unroll
     for(int r = 0; r < CS_ITEMS; ++r) {
-        cnt[r] = base + r < ncells ? cellTab[base + r].y : 0u;
+        cnt[r] = base + r < ncells ? cellCnt[base + r] : 0u;
         sum += cnt[r];
     }
     uint32_t x = sum; // inclusive scan of the per-thread sums over the warp, then over the warps
@@ -369,6 +381,7 @@ k_cell_scan_apply(uint2* __restrict__ cellTab, uint32_t ncells, const uint32_t* 
             const uint32_t c = cnt[r];
             cellTab[base + r] = c ? make_uint2(off, off + c) : make_uint2(0u, 0u);
             if(c) {
+                cellCnt[base + r] = 0u; // ready for the next count
                 const uint32_t key = base + r;
                 const int      cx = static_cast<int>(key % static_cast<uint32_t>(P.nx));
                 const int      t  = static_cast<int>(key / static_cast<uint32_t>(P.nx));
