@@ -276,6 +276,33 @@ def test_host_buffer_step_roundtrip(sf, ob):
     orc.close()
 
 
+def test_fused_binning_is_dropped_when_the_state_changes_behind_it(sf, ob):
+    """On one GPU the integrate kernel bins the new positions for the next substep (cellCnt / keys / ranks), and the
+    next resident substep starts at the cell scan.  Anything that replaces the positions in between -- a host-buffer
+    step, makeReady after a parameter change, a stop / start of the frame driver -- must drop that binning: resident
+    and host-buffer substeps interleaved, with a makeReady in the middle, equal the oracle's uninterrupted run."""
+    gpu, orc, pos = make_pair(sf, ob, "DoubleDambreak", 32)
+    for _ in range(5):  # resident: the first substep bins with k_hash_count, the others reuse the integrate kernel's
+        assert gpu.advanceFrame() == orc.advance()
+    x, v = gpu.getParticles().copy(), gpu.getVelocity().copy()
+    assert exact(x, orc.positions()) and exact(v, orc.velocities())
+    # host-buffer steps on a state that is NOT the resident one any more: one oracle substep applied twice over
+    for _ in range(3):
+        dto = orc.advance()
+        assert gpu.stepHost(x, v) == dto
+        assert exact(x, orc.positions()) and exact(v, orc.velocities())
+    for _ in range(4):  # resident again (the state of the last host step is on the device)
+        assert gpu.advanceFrame() == orc.advance()
+    assert exact(gpu.getParticles(), orc.positions()) and exact(gpu.getVelocity(), orc.velocities())
+    gpu.makeReady()  # Simulator::doSimulation calls it on every start (Simulator.cpp:42): state kept, binning redone
+    for _ in range(4):
+        assert gpu.advanceFrame() == orc.advance()
+    assert exact(gpu.getParticles(), orc.positions()) and exact(gpu.getVelocity(), orc.velocities())
+    assert exact(gpu.density(), orc.density()) and exact(gpu.cellIndex(), orc.cell_index())
+    gpu.close()
+    orc.close()
+
+
 def test_host_buffer_step_validates_the_domain_every_call(sf):
     """The steady-state path of sf_step_host (same particle count as the previous call) checks the box on the device:
     an out-of-box or non-finite position is SF_ERR_DOMAIN, as in sf_upload_particles -- not a silently wrong step."""
