@@ -9,4 +9,4 @@ SF_SLAB_TRACE=1 timeout 1200 $TR bench.py --gpus 8 --no-cpu-baseline > gpurun_ou
 if [ "$2" = "strong" ]; then
   SF_SLAB_TRACE=1 timeout 900 $TR bench.py --gpus 8 --no-cpu-baseline --workload doubledambreak_8m > gpurun_out/${tag}_bench_strong_n8.log 2>&1; echo "rc=$?" >> gpurun_out/${tag}_bench_strong_n8.log
 fi
-for f in ${tag}_bench_n8 ${tag}_bench_strong_n8; do [ -f gpurun_out/$f.log ] && { echo "== $f"; grep -v "^\[W\|^W0\|^\*\*\*\|OMP_NUM" gpurun_out/$f.log | cut -c1-1900 | tail -14; }; done
+for f in ${tag}_bench_n8 ${tag}_bench_strong_n8; do if [ -f gpurun_out/$f.log ]; then echo "== $f"; grep -v "^\[W\|^W0\|OMP_NUM" gpurun_out/$f.log | cut -c1-1900 | tail -14; fi; done; exit 0
