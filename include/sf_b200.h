@@ -164,8 +164,9 @@ typedef enum sf_field {
     SF_FIELD_LIST_TABLE_INDEX = 11 /* uint32[sum] kernel-table index min(trunc(sqrt(d2)*invStep), 10000) per list entry (A.2) */
 } sf_field;
 int sf_set_capture(sf_solver* s, int on);                         /* extra per-step stores for ACCEL */
-/* Entries per particle of the neighbour list the density pass builds (default 96; a rest-density particle has 32-40
- * neighbours).  Particles with more take the cell-traversal path in all three passes: slower, same bits.  Before the
+/* Entries per particle of the neighbour list the density pass builds (default 64 = 256 bytes per particle; a
+ * rest-density particle has 28-35 fluid neighbours, the fullest of any developed BASELINE state 48; the run time does not
+ * depend on it).  Particles with more take the cell-traversal path in all three passes: slower, same bits.  Before the
  * first upload only. */
 int sf_set_list_capacity(sf_solver* s, int kmax);
 int sf_field_size(sf_solver* s, int field, uint64_t* bytes_out);

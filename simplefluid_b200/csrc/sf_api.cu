@@ -47,7 +47,7 @@ struct sf_solver {
     std::string  lastError;
 
     uint32_t   n = 0, cap = 0, npad = 0;
-    int        kmax = 96;
+    int        kmax = 64; // list rows per particle: 47-48 is the most any developed BASELINE state needs (profiles/r02_d_config_sweep.log)
     int32_t    grid[3] = { 0, 0, 0 };
     uint64_t   ncells = 0, cellCap = 0;
     bool       ready = false, uploaded = false, capture = false;

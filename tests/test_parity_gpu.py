@@ -18,6 +18,9 @@ pytestmark = pytest.mark.gpu
 REL_TOL = 1e-5  # north_star: per-particle density, pressure, acceleration after one step
 
 
+LIST_CAPACITY = 64  # default rows per particle of the production neighbour list (sf_set_list_capacity)
+
+
 def rel_err(a, b):
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
@@ -29,12 +32,14 @@ def exact(a, b):
     return np.array_equal(np.asarray(a), np.asarray(b))
 
 
-def make_pair(sf, ob, scene, res, seed=0, capture=True, pos=None, vel=None, **over):
+def make_pair(sf, ob, scene, res, seed=0, capture=True, pos=None, vel=None, list_capacity=None, **over):
     p = sf.default_params(res, scene, **over)
     po = ob.default_params(res, scene, **over)
     if pos is None:
         pos = sf.scene_generate(p)
     gpu = sf.SPHSolver(p)
+    if list_capacity:
+        gpu.setListCapacity(list_capacity)  # before the first upload
     gpu.setParticles(pos, vel)
     gpu.generateBoundaryParticles(seed)
     gpu.setCapture(capture)
@@ -432,7 +437,7 @@ def test_full_size_properties_double_dambreak_8m(sf):
             cell = gpu.cellIndex()
             assert np.all(np.diff(cell[perm].astype(np.int64)) >= 0)  # sorted slots are in key order
             cnt = gpu.field(4)
-            assert cnt.max() <= 96 and int(cnt.astype(np.int64).sum()) % 2 == 0  # symmetric relation: even pair count
+            assert cnt.max() <= LIST_CAPACITY and int(cnt.astype(np.int64).sum()) % 2 == 0  # symmetric relation: even pair count
             r = p.particleRadius
             assert x.min() >= -1 + r and x.max() <= 1 - r and np.isfinite(x).all()
         gpu.close()
@@ -574,7 +579,7 @@ def test_compressed_flow_bricks_are_processed_in_parts(sf, ob, per_cell):
     lo = np.array([-1.0 + h, -1.0 + 3 * h, -1.0 + 3 * h])
     pos = (rng.random((n, 3)) * (cells * h) + lo).astype(np.float32)
     vel = (rng.standard_normal((n, 3)) * 0.05).astype(np.float32)
-    gpu, orc, _ = make_pair(sf, ob, "CubeDrop", 16, pos=pos, vel=vel)
+    gpu, orc, _ = make_pair(sf, ob, "CubeDrop", 16, pos=pos, vel=vel, list_capacity=96)  # 18 per cell: 76 neighbours on average
     inv_step = float(sf.binding.build_tables(p)[2][2])
     for _ in range(2):
         x0 = orc.positions()
@@ -603,8 +608,8 @@ def test_production_list_crowded(sf, ob):
     assert orc.advance() == gpu.advanceFrame()
     cnt, raw, ids, tab = gpu.productionLists()
     check_production_list(gpu, pos, ocnt, oids, inv_step)
-    assert (cnt < 0).any() and (cnt >= 0).any()  # some lists overflow the default capacity of 96, most do not
-    assert np.array_equal(cnt < 0, ocnt > 96)  # no walls near: the list holds fluid neighbours only
+    assert (cnt < 0).any() and (cnt >= 0).any()  # some lists overflow the default capacity, most do not
+    assert np.array_equal(cnt < 0, ocnt > LIST_CAPACITY)  # no walls near: the list holds fluid neighbours only
     assert (tab == 0).any()  # the coincident pair
     gpu.close()
     orc.close()
