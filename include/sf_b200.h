@@ -178,10 +178,9 @@ int sf_grid_dims(sf_solver* s, int32_t n3[3]);                     /* Grid3D::se
  * counts, particles without a list, particles resident on this rank}.  Synchronises. */
 int sf_diagnostics(sf_solver* s, uint64_t out[8]);
 
-/* Development counters of instrumented builds (make EXTRA=-DSF_EXP_WAITSTAT), density pass, cumulative: consumer-warp
- * cycles waiting for a staged brick, refills counted, consumer cycles in the exact phase, consumer cycles in total,
- * producer cycles per refill (buffer free -> brick released), of which waiting for the TMA copies, of which converting,
- * (unused).  Zeros in a normal build. */
+/* Development counters of instrumented builds (make EXTRA=-DSF_EXP_WAITSTAT), cumulative: density consumer-warp cycles
+ * waiting for a staged brick, refills counted, density consumer cycles in the exact phase, density consumer cycles in
+ * total, producer cycles waiting for a free staging buffer, (unused x3).  Zeros in a normal build. */
 int sf_debug_counters(sf_solver* s, uint64_t out[8]);
 
 /* ---- measurement ---------------------------------------------------------------------------- */

@@ -71,9 +71,9 @@ struct DevState {
     unsigned brickCount;  // non-empty bricks of this substep
     unsigned cursor[6];   // work cursors of the persistent pair kernels (density, force, viscosity edge / interior, Shepard)
     unsigned fallbackBricks, fallbackParticles; // diagnostics: halos that did not fit smem / lists that overflowed
-    // SF_EXP_WAITSTAT builds, density pass: consumer-warp cycles waiting for a brick / refills counted / consumer cycles in
-    // the exact phase / consumer cycles in total / producer cycles from "buffer free" to "brick released" (refill latency),
-    // of which waiting for the TMA copies / converting to half precision / (unused)
+    // SF_EXP_WAITSTAT builds: density consumer-warp cycles waiting for a brick / refills counted (producers of all pair
+    // kernels) / density consumer cycles in the exact phase / density consumer cycles in total / producer cycles waiting
+    // for a free staging buffer / (unused x3)
     unsigned long long dbg[8];
 };
 

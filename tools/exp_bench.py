@@ -39,6 +39,5 @@ dbg = g.debugCounters()
 if dbg[3]:
     print(f"   density consumer warps: waiting for a brick {dbg[0] / dbg[3] * 100:.1f} %, exact phase {dbg[2] / dbg[3] * 100:.1f} % of their cycles")
     if dbg[1]:
-        print(f"   density producer, per refill: {dbg[4] / dbg[1]:.0f} cycles from buffer free to brick released = {dbg[5] / dbg[1]:.0f} issuing + waiting for the TMA copies"
-              f" + {dbg[6] / dbg[1]:.0f} converting; consumer warp-cycles per brick {dbg[3] / dbg[1]:.0f}")
+        print(f"   producers (all pair kernels), per refill: {dbg[4] / dbg[1]:.0f} cycles waiting for a free staging buffer; {dbg[1]} refills")
 g.close()
