@@ -166,8 +166,8 @@ typedef enum sf_field {
 int sf_set_capture(sf_solver* s, int on);                         /* extra per-step stores for ACCEL */
 /* Entries per particle of the neighbour list the density pass builds (default 64 = 256 bytes per particle; a
  * rest-density particle has 28-35 fluid neighbours, the fullest of any developed BASELINE state 48; the run time does not
- * depend on it).  Particles with more take the cell-traversal path in all three passes: slower, same bits.  Before the
- * first upload only. */
+ * depend on it; rounded up to a multiple of four).  Particles with more take the cell-traversal path in all three
+ * passes: slower, same bits.  Before the first upload only. */
 int sf_set_list_capacity(sf_solver* s, int kmax);
 int sf_field_size(sf_solver* s, int field, uint64_t* bytes_out);
 int sf_download_field(sf_solver* s, int field, void* out, uint64_t bytes);

@@ -140,6 +140,10 @@ void drop_graph(sf_solver* s)
     }
 }
 
+// The list walkers request rows four at a time (walk_list, sf_pairs.cuh): the capacity is a multiple of four, so that
+// "the next four rows lie inside the column" is one comparison
+int round_list_capacity(int kmax) { return std::min((kmax + 3) & ~3, 16380); }
+
 // posA is about to change behind the integrate kernel's back (or the grid is): forget the fused binning
 int invalidate_binning(sf_solver* s)
 {
@@ -853,7 +857,7 @@ int sf_create(const sf_params* p, int device, sf_solver** out)
     s->stream = s->ownStream;
     s->useGraph = std::getenv("SF_NO_GRAPH") == nullptr;
     if(const char* m = std::getenv("SF_SORT")) s->countSort = std::strcmp(m, "radix") != 0;
-    if(const char* m = std::getenv("SF_KMAX")) s->kmax = std::min(std::max(std::atoi(m), 8), 16383);
+    if(const char* m = std::getenv("SF_KMAX")) s->kmax = round_list_capacity(std::min(std::max(std::atoi(m), 8), 16380));
     s->occDensity = std::max(s->occDensity, 1);
     s->occForce   = std::max(s->occForce, 1);
     s->occVisc    = std::max(s->occVisc, 1);
@@ -1326,7 +1330,7 @@ int sf_set_list_capacity(sf_solver* s, int kmax)
 {
     if(!s || kmax < 8 || kmax > 16383) return SF_ERR_INVALID;
     if(s->B.posA) return fail(s, SF_ERR_INVALID, "sf_set_list_capacity: call before the first upload");
-    s->kmax = kmax;
+    s->kmax = round_list_capacity(kmax);
     return SF_OK;
 }
 

@@ -1,0 +1,228 @@
+"""CPU restatements of the index logic the round-2 pair kernels rely on (simplefluid_b200/csrc/sf_pairs.cuh,
+sf_kernels.cuh), operation by operation, checked exhaustively or under random inputs:
+
+  * the neighbour-list entry codec (list_entry_fluid / list_entry_wall / entry_*_off): the two shared-memory byte
+    offsets a walker needs, packed into 32 bits;
+  * walk_list: the software pipeline of the list walkers (rows requested unconditionally inside the column, two register
+    sets, tail without a further request) visits the first nF entries exactly once, in order, and never reads a row
+    outside the column;
+  * the counted exact phase of k_density_brick (non-empty windows pooled per lane, sentinel entry, refill predicated on
+    an empty mask, exactly nh iterations): hits come out in ascending (window, slot) order, nothing is evaluated twice,
+    the pool is never indexed beyond its kPool + 2 entries;
+  * count_into_cell (warp-aggregated arrival ranks of the counting sort, also run by the integrate kernel): the ranks
+    of the particles of a cell are a permutation of 0 .. count-1 whatever the order in which the warps arrive, and the
+    scatter they drive is a bijection onto the sorted slots.
+
+These are models of the kernels' control flow, not of their arithmetic; the bit-exactness of the arithmetic is what the
+GPU parity tests check."""
+import random
+
+import numpy as np
+import pytest
+
+K_STAGE_CAP = 3584   # halo particles per staging buffer (kStageCap)
+K_TAB = 10000        # last kernel-table index (kTab)
+K_POOL = 12          # windows pooled per drain (kPool)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def entry_fluid(halo, tab):
+    return ((tab << 18) + (halo << 4)) & 0xFFFFFFFF
+
+
+def entry_wall(b, tab):
+    return ((tab << 18) | b) & 0xFFFFFFFF
+
+
+def test_list_entry_codec_roundtrip_and_ranges():
+    halo = np.arange(K_STAGE_CAP + 512, dtype=np.uint64)  # up to the static bound of 4096
+    halo = halo[halo < 4096]
+    for tab in (0, 1, 2499, 9999, K_TAB):
+        e = (np.uint64(tab) << np.uint64(18)) + (halo << np.uint64(4))
+        assert (e < 2**32).all()
+        assert np.array_equal(e & np.uint64(0xFFFF), halo * 16)   # byte offset of the float4 in the staging buffer
+        assert np.array_equal(e >> np.uint64(16), np.full_like(halo, 4 * tab))  # byte offset in the table
+    # the largest offsets stay inside a staging buffer / the table
+    assert (entry_fluid(K_STAGE_CAP - 1, K_TAB) & 0xFFFF) + 16 <= K_STAGE_CAP * 16
+    assert (entry_fluid(K_STAGE_CAP - 1, K_TAB) >> 16) + 4 <= (K_TAB + 4) * 4
+    for b in (0, 1, 62, 63, 1000):  # wall entries: index of the wall particle, not multiplied
+        e = entry_wall(b, 777)
+        assert e & 0xFFFF == b and e >> 16 == 4 * 777
+    # the decoder of the parity download
+    e = entry_fluid(1234, 5678)
+    assert (e & 0xFFFF) >> 4 == 1234 and (e >> 16) >> 2 == 5678
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def walk_list_model(column, nF, kmax):
+    """walk_list of sf_pairs.cuh: `column` is the list column (kmax rows); returns the entries passed to f, in order,
+    and the set of rows that were read."""
+    read = set()
+
+    def load4(row):
+        out = []
+        for r in range(row, row + 4):
+            assert 0 <= r < kmax, f"row {r} outside the column of {kmax} rows"
+            read.add(r)
+            out.append(column[r])
+        return out
+
+    c = load4(0)  # the caller's rows 0..3, requested before the count is known (every column has >= 8 rows)
+    d = [None] * 4
+    out = []
+    lp = 0
+    k = 0
+    sets = [c, d]
+    cur = 0
+    while True:
+        e = sets[cur]
+        if k + 4 > nF:  # tail: at most three entries, already in registers
+            r = nF - k
+            for i in range(r):
+                out.append(e[i])
+            break
+        lp += 4
+        if k + 8 <= kmax:  # unconditional inside the column
+            sets[cur ^ 1][:] = load4(lp)
+        out.extend(e)
+        k += 4
+        cur ^= 1
+    return out, read
+
+
+def test_walk_list_needs_a_capacity_that_is_a_multiple_of_four():
+    """Why sf_set_list_capacity rounds up: with 9 rows the guard `k + 8 <= kmax` never requests row 8."""
+    column = list(range(9))
+    out, _ = walk_list_model(column, 9, 9)
+    assert out != column  # (the model of the hazard; the library never runs with such a capacity)
+
+
+@pytest.mark.parametrize("kmax", [8, 12, 24, 64, 96, 100])
+def test_walk_list_visits_every_entry_once_in_order(kmax):
+    column = list(range(1000, 1000 + kmax))
+    for nF in range(0, kmax + 1):
+        out, read = walk_list_model(column, nF, kmax)
+        assert out == column[:nF], (kmax, nF)
+        assert max(read) < kmax
+        # the pipeline never runs more than two batches ahead of what it consumes
+        assert max(read) <= min(kmax - 1, (nF // 4) * 4 + 7)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def counted_exact_phase_model(window_masks, window_bases, self_slot):
+    """Phase A + drain of k_density_brick for ONE lane.  window_masks / window_bases: the hit mask and first halo slot
+    of every window of the lane's nine candidate runs, in traversal order (a mask may be 0).  Returns the halo slots
+    evaluated, in order."""
+    pool = [None] * (K_POOL + 2)
+    evaluated = []
+    ne = nh = nwin = 0
+
+    def ffs(x):
+        return (x & -x).bit_length()
+
+    def drain():
+        nonlocal ne, nh, nwin
+        if nh:
+            pool[ne] = (1, self_slot)  # sentinel
+            cur, wb = pool[0]
+            ei = 1
+            e = pool[1]  # may be stale / None: only used after the window in `cur` is exhausted
+            j = wb + ffs(cur) - 1
+            cur &= cur - 1
+            x = j  # "position" of the current hit
+            n = nh
+            while True:
+                # SF_HIT_STEP: evaluate x, extract the next hit
+                evaluated.append(x)
+                if cur == 0:
+                    assert e is not None and ei + 1 < len(pool), "refill beyond the sentinel"
+                    cur, wb = e
+                    ei += 1
+                    e = pool[ei]
+                jn = wb + ffs(cur) - 1
+                cur &= cur - 1
+                x = jn
+                n -= 1
+                if n == 0:
+                    break
+            # what was extracted last and never evaluated is the sentinel's slot, or a hit of... no: exactly the sentinel
+            assert x == self_slot or nh == 0
+        for i in range(len(pool)):
+            pool[i] = pool[i]  # (entries stay: stale ones must never be consumed)
+        ne = nwin = 0
+        nh = 0
+
+    for mask, base in zip(window_masks, window_bases):
+        pool[ne] = (mask, base)  # overwritten by the next window when empty
+        ne += 1 if mask else 0
+        nh += bin(mask).count("1")
+        nwin += 1
+        if nwin == K_POOL:
+            drain()
+    if nwin:
+        drain()
+    return evaluated
+
+
+def test_counted_exact_phase_walks_the_hits_in_traversal_order():
+    rng = random.Random(5)
+    for trial in range(3000):
+        nw = rng.choice([1, 2, 9, 10, 11, 12, 13, 18, 24, 25, 40])
+        masks, bases = [], []
+        base = rng.randrange(0, 50)
+        for _ in range(nw):
+            density = rng.choice([0.0, 0.05, 0.15, 0.5, 1.0])
+            m = 0
+            for b in range(32):
+                if rng.random() < density:
+                    m |= 1 << b
+            masks.append(m)
+            bases.append(base)
+            base += rng.randrange(32, 120)  # windows of later rows lie at higher halo slots
+        self_slot = 100000 + trial
+        want = [b + i for m, b in zip(masks, bases) for i in range(32) if m >> i & 1]
+        got = counted_exact_phase_model(masks, bases, self_slot)
+        assert got == want
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def count_into_cell_model(keys_by_warp, order, ncells):
+    """k_hash_count / the fused part of k_visc_brick: warps arrive in `order`; inside a warp one atomicAdd per distinct
+    key (leader = lowest lane with that key) and rank = base + number of lower lanes with the same key."""
+    cell_cnt = np.zeros(ncells, dtype=np.int64)
+    ranks = {}
+    for w in order:
+        keys = keys_by_warp[w]
+        base_of = {}
+        for lane, key in enumerate(keys):
+            if key is None:  # inactive lane: invalid key, no atomic
+                continue
+            if key not in base_of:
+                peers = sum(1 for k in keys if k == key)
+                base_of[key] = int(cell_cnt[key])
+                cell_cnt[key] += peers
+            lower = sum(1 for k in keys[:lane] if k == key)
+            ranks[(w, lane)] = base_of[key] + lower
+    return cell_cnt, ranks
+
+
+def test_arrival_ranks_are_a_permutation_per_cell_for_any_warp_order():
+    rng = random.Random(9)
+    for _ in range(200):
+        ncells = rng.choice([1, 3, 17, 64])
+        nwarps = rng.randrange(1, 12)
+        keys_by_warp = [[(rng.randrange(ncells) if rng.random() < 0.9 else None) for _ in range(32)] for _ in range(nwarps)]
+        order = list(range(nwarps))
+        rng.shuffle(order)
+        cnt, ranks = count_into_cell_model(keys_by_warp, order, ncells)
+        begin = np.concatenate(([0], np.cumsum(cnt)[:-1]))  # the exclusive scan of k_cell_scan_*
+        per_cell = {}
+        slots = []
+        for (w, lane), r in ranks.items():
+            key = keys_by_warp[w][lane]
+            per_cell.setdefault(key, []).append(r)
+            slots.append(int(begin[key]) + r)  # k_count_scatter: dst = cellTab[key].x + rank
+        for key, rs in per_cell.items():
+            assert sorted(rs) == list(range(int(cnt[key])))
+        n = sum(1 for ks in keys_by_warp for k in ks if k is not None)
+        assert sorted(slots) == list(range(n))  # a bijection onto the sorted slots

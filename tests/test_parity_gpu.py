@@ -540,13 +540,14 @@ def test_production_neighbor_list_matches_oracle(sf, ob, scene, res):
     orc.close()
 
 
-def test_production_list_capacity_overflow_falls_back(sf, ob):
+@pytest.mark.parametrize("capacity,effective", [(24, 24), (26, 28)])  # rounded up to a multiple of four (walk_list requests four rows at a time)
+def test_production_list_capacity_overflow_falls_back(sf, ob, capacity, effective):
     """kmax = 24 on a lattice whose interior particles have 32 neighbours: those lists overflow, the particles take
     the traversal path in all three passes (same bits), the others keep their lists."""
     p = sf.default_params(24, "CubeDrop")
     pos = sf.scene_generate(p)
     gpu = sf.SPHSolver(p)
-    gpu.setListCapacity(24)
+    gpu.setListCapacity(capacity)
     gpu.setParticles(pos)
     gpu.generateBoundaryParticles(0)
     gpu.setCapture(True)
@@ -558,7 +559,7 @@ def test_production_list_capacity_overflow_falls_back(sf, ob):
         ocnt, oids = orc.neighbors()
         assert orc.advance() == gpu.advanceFrame()
         check_step_fields(gpu, orc, ocnt, oids)
-        expect = ocnt > 24  # fluid neighbours only here: the cube is far from every wall
+        expect = ocnt > effective  # fluid neighbours only here: the cube is far from every wall
         assert expect.any() and not expect.all()
         check_production_list(gpu, x0, ocnt, oids, inv_step, expect_nolist=expect)
         assert gpu.diagnostics()["particles_without_list"] == int(expect.sum())
