@@ -761,38 +761,51 @@ int slab_exchange(sf_solver* s, uint32_t n, uint32_t nSlots)
 // =================================================================================================
 extern "C" {
 
+// No C++ exception crosses the C boundary (include/sf_b200.h): every entry point that returns a status is a
+// function-try-block; std::bad_alloc / std::length_error of a host container become SF_ERR_OOM, anything else
+// SF_ERR_INVALID, with the text in sf_last_error.
+#define SF_NOTHROW(S, NAME)                                                                                     \
+    catch(const std::bad_alloc& e) { return fail((S), SF_ERR_OOM, std::string(NAME ": ") + e.what()); }         \
+    catch(const std::length_error& e) { return fail((S), SF_ERR_OOM, std::string(NAME ": ") + e.what()); }      \
+    catch(const std::exception& e) { return fail((S), SF_ERR_INVALID, std::string(NAME ": ") + e.what()); }     \
+    catch(...) { return fail((S), SF_ERR_INVALID, NAME ": unknown exception"); }
+
 int sf_params_default(sf_params* p)
-{
+try {
     if(!p) return SF_ERR_INVALID;
     params_default(*p);
     return SF_OK;
 }
+SF_NOTHROW(nullptr, "sf_params_default")
 
 int sf_params_update(sf_params* p)
-{
+try {
     if(!p) return SF_ERR_INVALID;
     params_update(*p);
     return SF_OK;
 }
+SF_NOTHROW(nullptr, "sf_params_update")
 
 int sf_params_set_resolution(sf_params* p, float resolution)
-{
+try {
     if(!p || !(resolution > 0.f)) return SF_ERR_INVALID;
     p->kernelRadius = 2.0f / resolution; // Source/Controller.cpp:55
     params_update(*p);
     return SF_OK;
 }
+SF_NOTHROW(nullptr, "sf_params_set_resolution")
 
 int sf_scene_generate(const sf_params* p, int scene, float* pos_xyz, uint64_t cap, uint64_t* n_out)
-{
+try {
     if(!p || scene < 0 || scene > 3) return SF_ERR_INVALID;
     const uint64_t n = scene_generate(*p, scene, pos_xyz, cap);
     if(n_out) *n_out = n;
     return SF_OK;
 }
+SF_NOTHROW(nullptr, "sf_scene_generate")
 
 int sf_build_tables(const sf_params* p, float* cubic_w10001, float* spiky_grad10001, float* consts3)
-{
+try {
     if(!p) return SF_ERR_INVALID;
     KernelTables t;
     build_tables(p->kernelRadius, t);
@@ -805,9 +818,10 @@ int sf_build_tables(const sf_params* p, float* cubic_w10001, float* spiky_grad10
     }
     return SF_OK;
 }
+SF_NOTHROW(nullptr, "sf_build_tables")
 
 int sf_boundary_generate(const sf_params* p, uint32_t seed, int wall, float* xyz, uint32_t cap, uint32_t* n_out)
-{
+try {
     if(!p || wall < 0 || wall > 5) return SF_ERR_INVALID;
     std::vector<float> walls[6];
     generate_boundary(*p, seed, walls);
@@ -816,9 +830,10 @@ int sf_boundary_generate(const sf_params* p, uint32_t seed, int wall, float* xyz
     if(xyz) std::memcpy(xyz, walls[wall].data(), sizeof(float) * 3 * std::min(n, cap));
     return SF_OK;
 }
+SF_NOTHROW(nullptr, "sf_boundary_generate")
 
 int sf_create(const sf_params* p, int device, sf_solver** out)
-{
+try {
     if(!p || !out) return fail(nullptr, SF_ERR_INVALID, "null argument");
     *out = nullptr;
     int         count = 0;
@@ -864,6 +879,7 @@ int sf_create(const sf_params* p, int device, sf_solver** out)
     *out = s;
     return SF_OK;
 }
+SF_NOTHROW(nullptr, "sf_create")
 
 void sf_destroy(sf_solver* s)
 {
@@ -926,22 +942,24 @@ void sf_destroy(sf_solver* s)
 const char* sf_last_error(sf_solver* s) { return s ? s->lastError.c_str() : g_createError.c_str(); }
 
 int sf_set_params(sf_solver* s, const sf_params* p)
-{
+try {
     if(!s || !p) return SF_ERR_INVALID;
     s->params = *p;
     s->ready  = false; // tables / grid depend on kernelRadius: makeReady again (Simulator.cpp:42)
     return SF_OK;
 }
+SF_NOTHROW(s, "sf_set_params")
 
 int sf_get_params(sf_solver* s, sf_params* p)
-{
+try {
     if(!s || !p) return SF_ERR_INVALID;
     *p = s->params;
     return SF_OK;
 }
+SF_NOTHROW(s, "sf_get_params")
 
 int sf_set_stream(sf_solver* s, void* cuda_stream)
-{
+try {
     if(!s) return SF_ERR_INVALID;
     cudaSetDevice(s->device);
     cudaStreamSynchronize(s->stream);
@@ -949,9 +967,10 @@ int sf_set_stream(sf_solver* s, void* cuda_stream)
     drop_graph(s);
     return SF_OK;
 }
+SF_NOTHROW(s, "sf_set_stream")
 
 int sf_upload_particles(sf_solver* s, const float* pos_xyz, const float* vel_xyz, uint32_t n)
-{
+try {
     if(!s || (!pos_xyz && n)) return SF_ERR_INVALID;
     SF_CUDA(s, cudaSetDevice(s->device));
     // domain check: the pair loops assume the unclamped cell of A.6 equals the binned cell of A.7
@@ -983,13 +1002,15 @@ int sf_upload_particles(sf_solver* s, const float* pos_xyz, const float* vel_xyz
     s->ready    = false;
     return SF_OK;
 }
+SF_NOTHROW(s, "sf_upload_particles")
 
 int sf_num_particles(sf_solver* s, uint32_t* n_out)
-{
+try {
     if(!s || !n_out) return SF_ERR_INVALID;
     *n_out = s->n;
     return SF_OK;
 }
+SF_NOTHROW(s, "sf_num_particles")
 
 static int download_xyz(sf_solver* s, const float4* src, float* out)
 {
@@ -1011,34 +1032,37 @@ int sf_download_positions(sf_solver* s, float* pos_xyz) { return download_xyz(s,
 int sf_download_velocities(sf_solver* s, float* vel_xyz) { return download_xyz(s, s ? s->B.velA : nullptr, vel_xyz); }
 
 int sf_generate_boundary(sf_solver* s, uint32_t seed)
-{
+try {
     if(!s) return SF_ERR_INVALID;
     generate_boundary(s->params, seed, s->walls);
     s->wallsSet = true;
     s->ready    = false;
     return SF_OK;
 }
+SF_NOTHROW(s, "sf_generate_boundary")
 
 int sf_set_boundary_particles(sf_solver* s, int wall, const float* xyz, uint32_t n)
-{
+try {
     if(!s || wall < 0 || wall > 5 || (!xyz && n)) return SF_ERR_INVALID;
     s->walls[wall].assign(xyz, xyz + 3 * static_cast<size_t>(n));
     s->wallsSet = true;
     s->ready    = false;
     return SF_OK;
 }
+SF_NOTHROW(s, "sf_set_boundary_particles")
 
 int sf_get_boundary_particles(sf_solver* s, int wall, float* xyz, uint32_t cap, uint32_t* n_out)
-{
+try {
     if(!s || wall < 0 || wall > 5) return SF_ERR_INVALID;
     const uint32_t n = static_cast<uint32_t>(s->walls[wall].size() / 3);
     if(n_out) *n_out = n;
     if(xyz) std::memcpy(xyz, s->walls[wall].data(), sizeof(float) * 3 * std::min(n, cap));
     return SF_OK;
 }
+SF_NOTHROW(s, "sf_get_boundary_particles")
 
 int sf_make_ready(sf_solver* s)
-{
+try {
     if(!s) return SF_ERR_INVALID;
     if(!s->uploaded) return fail(s, SF_ERR_INVALID, "sf_make_ready: upload particles first");
     SF_CUDA(s, cudaSetDevice(s->device));
@@ -1119,9 +1143,10 @@ int sf_make_ready(sf_solver* s)
     s->ready = true;
     return SF_OK;
 }
+SF_NOTHROW(s, "sf_make_ready")
 
 int sf_advance_frame(sf_solver* s, float* dt_out)
-{
+try {
     int rc = require_ready(s);
     if(rc) return rc;
     SF_CUDA(s, cudaSetDevice(s->device));
@@ -1132,9 +1157,10 @@ int sf_advance_frame(sf_solver* s, float* dt_out)
     if(dt_out) *dt_out = s->hostState->dt;
     return SF_OK;
 }
+SF_NOTHROW(s, "sf_advance_frame")
 
 int sf_advance_steps(sf_solver* s, uint32_t nsteps, float* time_out)
-{
+try {
     int rc = require_ready(s);
     if(rc) return rc;
     SF_CUDA(s, cudaSetDevice(s->device));
@@ -1155,9 +1181,10 @@ int sf_advance_steps(sf_solver* s, uint32_t nsteps, float* time_out)
     }
     return SF_OK;
 }
+SF_NOTHROW(s, "sf_advance_steps")
 
 int sf_advance_frame_time(sf_solver* s, double frame_time, float* time_out, uint32_t* nsteps_out)
-{
+try {
     int rc = require_ready(s);
     if(rc) return rc;
     if(!(frame_time > 0.0)) return fail(s, SF_ERR_INVALID, "frame_time must be positive");
@@ -1212,17 +1239,19 @@ int sf_advance_frame_time(sf_solver* s, double frame_time, float* time_out, uint
     SF_CUDA(s, cudaStreamSynchronize(s->stream));
     return SF_OK;
 }
+SF_NOTHROW(s, "sf_advance_frame_time")
 
 int sf_synchronize(sf_solver* s)
-{
+try {
     if(!s) return SF_ERR_INVALID;
     SF_CUDA(s, cudaSetDevice(s->device));
     SF_CUDA(s, cudaStreamSynchronize(s->stream));
     return SF_OK;
 }
+SF_NOTHROW(s, "sf_synchronize")
 
 int sf_step_host(sf_solver* s, float* pos_xyz, float* vel_xyz, uint32_t n, float* dt_out)
-{
+try {
     if(!s || !pos_xyz || !vel_xyz) return SF_ERR_INVALID;
     if(s->slab.on) return fail(s, SF_ERR_INVALID, "slab mode: use sf_upload_local / sf_advance_frame / sf_download_local");
     const bool sameShape = s->uploaded && s->ready && n == s->n && n > 0;
@@ -1295,9 +1324,10 @@ int sf_step_host(sf_solver* s, float* pos_xyz, float* vel_xyz, uint32_t n, float
     if(dt_out) *dt_out = s->hostState->dt;
     return SF_OK;
 }
+SF_NOTHROW(s, "sf_step_host")
 
 int sf_host_alloc(uint64_t bytes, void** out)
-{
+try {
     if(!out) return SF_ERR_INVALID;
     *out = nullptr;
     if(bytes == 0) return SF_OK;
@@ -1305,17 +1335,19 @@ int sf_host_alloc(uint64_t bytes, void** out)
     if(e != cudaSuccess) return fail(nullptr, e == cudaErrorMemoryAllocation ? SF_ERR_OOM : SF_ERR_CUDA, std::string("cudaMallocHost: ") + cudaGetErrorString(e));
     return SF_OK;
 }
+SF_NOTHROW(nullptr, "sf_host_alloc")
 
 int sf_host_free(void* p)
-{
+try {
     if(!p) return SF_OK;
     const cudaError_t e = cudaFreeHost(p);
     if(e != cudaSuccess) return fail(nullptr, SF_ERR_CUDA, std::string("cudaFreeHost: ") + cudaGetErrorString(e));
     return SF_OK;
 }
+SF_NOTHROW(nullptr, "sf_host_free")
 
 int sf_debug_counters(sf_solver* s, uint64_t out[8])
-{
+try {
     int rc = require_ready(s);
     if(rc) return rc;
     if(!out) return SF_ERR_INVALID;
@@ -1325,30 +1357,34 @@ int sf_debug_counters(sf_solver* s, uint64_t out[8])
     for(int i = 0; i < 8; ++i) out[i] = s->hostState->dbg[i];
     return SF_OK;
 }
+SF_NOTHROW(s, "sf_debug_counters")
 
 int sf_set_list_capacity(sf_solver* s, int kmax)
-{
+try {
     if(!s || kmax < 8 || kmax > 16383) return SF_ERR_INVALID;
     if(s->B.posA) return fail(s, SF_ERR_INVALID, "sf_set_list_capacity: call before the first upload");
     s->kmax = round_list_capacity(kmax);
     return SF_OK;
 }
+SF_NOTHROW(s, "sf_set_list_capacity")
 
 int sf_set_capture(sf_solver* s, int on)
-{
+try {
     if(!s) return SF_ERR_INVALID;
     s->capture   = on != 0;
     s->P.capture = on ? 1 : 0;
     drop_graph(s);
     return SF_OK;
 }
+SF_NOTHROW(s, "sf_set_capture")
 
 int sf_grid_dims(sf_solver* s, int32_t n3[3])
-{
+try {
     if(!s || !n3) return SF_ERR_INVALID;
     grid_dims(s->params, n3);
     return SF_OK;
 }
+SF_NOTHROW(s, "sf_grid_dims")
 
 static int neighbor_lists_host(sf_solver* s, std::vector<uint32_t>& counts, std::vector<uint32_t>* ids)
 {
@@ -1431,7 +1467,7 @@ static int production_lists_host(sf_solver* s, std::vector<uint32_t>& counts, st
 }
 
 int sf_field_size(sf_solver* s, int field, uint64_t* bytes_out)
-{
+try {
     if(!s || !bytes_out) return SF_ERR_INVALID;
     const uint64_t n = s->n;
     switch(field) {
@@ -1474,9 +1510,10 @@ int sf_field_size(sf_solver* s, int field, uint64_t* bytes_out)
         default: return fail(s, SF_ERR_INVALID, "unknown field");
     }
 }
+SF_NOTHROW(s, "sf_field_size")
 
 int sf_download_field(sf_solver* s, int field, void* out, uint64_t bytes)
-{
+try {
     int rc = require_ready(s);
     if(rc) return rc;
     if(!out) return SF_ERR_INVALID;
@@ -1532,10 +1569,11 @@ int sf_download_field(sf_solver* s, int field, void* out, uint64_t bytes)
     SF_CUDA(s, cudaStreamSynchronize(s->stream));
     return SF_OK;
 }
+SF_NOTHROW(s, "sf_download_field")
 
 // ---- diagnostics of the last substep ---------------------------------------------------------------
 int sf_diagnostics(sf_solver* s, uint64_t out[8])
-{
+try {
     int rc = require_ready(s);
     if(rc) return rc;
     if(!out) return SF_ERR_INVALID;
@@ -1566,10 +1604,11 @@ int sf_diagnostics(sf_solver* s, uint64_t out[8])
     out[7] = s->n;
     return SF_OK;
 }
+SF_NOTHROW(s, "sf_diagnostics")
 
 // ---- measurement -------------------------------------------------------------------------------
 int sf_profile_enable(sf_solver* s, int on)
-{
+try {
     if(!s) return SF_ERR_INVALID;
     cudaSetDevice(s->device);
     if(!on) fold_pending(s);
@@ -1578,9 +1617,10 @@ int sf_profile_enable(sf_solver* s, int on)
     s->profiling = false;
     return SF_OK;
 }
+SF_NOTHROW(s, "sf_profile_enable")
 
 int sf_profile_reset(sf_solver* s)
-{
+try {
     if(!s) return SF_ERR_INVALID;
     cudaSetDevice(s->device);
     fold_pending(s);
@@ -1588,9 +1628,10 @@ int sf_profile_reset(sf_solver* s)
     std::memset(s->profLaunches, 0, sizeof(s->profLaunches));
     return SF_OK;
 }
+SF_NOTHROW(s, "sf_profile_reset")
 
 int sf_profile_get(sf_solver* s, char* names_buf, size_t names_cap, double* ms, uint64_t* launches, uint32_t cap, uint32_t* count_out)
-{
+try {
     if(!s) return SF_ERR_INVALID;
     cudaSetDevice(s->device);
     fold_pending(s);
@@ -1611,24 +1652,27 @@ int sf_profile_get(sf_solver* s, char* names_buf, size_t names_cap, double* ms, 
     if(count_out) *count_out = K_COUNT;
     return SF_OK;
 }
+SF_NOTHROW(s, "sf_profile_get")
 
 int sf_launch_count(sf_solver* s, uint64_t* n_out)
-{
+try {
     if(!s || !n_out) return SF_ERR_INVALID;
     *n_out = s->launches;
     return SF_OK;
 }
+SF_NOTHROW(s, "sf_launch_count")
 
 int sf_timer_start(sf_solver* s)
-{
+try {
     if(!s) return SF_ERR_INVALID;
     SF_CUDA(s, cudaSetDevice(s->device));
     SF_CUDA(s, cudaEventRecord(s->timerA, s->stream));
     return SF_OK;
 }
+SF_NOTHROW(s, "sf_timer_start")
 
 int sf_timer_stop(sf_solver* s, float* ms_out)
-{
+try {
     if(!s || !ms_out) return SF_ERR_INVALID;
     SF_CUDA(s, cudaSetDevice(s->device));
     SF_CUDA(s, cudaEventRecord(s->timerB, s->stream));
@@ -1637,13 +1681,14 @@ int sf_timer_stop(sf_solver* s, float* ms_out)
     if(s->slab.on && s->slab.tlLevel >= 2) slab_timeline_report(s); // SF_SLAB_TRACE=2: the region just timed
     return SF_OK;
 }
+SF_NOTHROW(s, "sf_timer_stop")
 
 // ---- renderer hand-off: asynchronous position snapshot -------------------
 // FluidRenderWidget::updateParticleData uploads the "Position" array once per particleChanged signal
 // (Source/FluidRenderWidget.cpp:204-221).  The snapshot is scattered to original order on the compute stream,
 // copied to the (ideally pinned) host buffer on a separate copy stream, and the solver keeps stepping meanwhile.
 int sf_snapshot_positions_async(sf_solver* s, float* host_xyz)
-{
+try {
     if(!s || !host_xyz) return SF_ERR_INVALID;
     if(!s->uploaded) return fail(s, SF_ERR_INVALID, "no particles uploaded");
     if(s->slab.on) return fail(s, SF_ERR_INVALID, "slab mode: use sf_download_owned");
@@ -1671,15 +1716,17 @@ int sf_snapshot_positions_async(sf_solver* s, float* host_xyz)
     SF_CUDA(s, cudaEventRecord(s->snapDone, s->snapStream));
     return SF_OK;
 }
+SF_NOTHROW(s, "sf_snapshot_positions_async")
 
 int sf_snapshot_wait(sf_solver* s)
-{
+try {
     if(!s) return SF_ERR_INVALID;
     if(!s->snapStream) return SF_OK;
     SF_CUDA(s, cudaSetDevice(s->device));
     SF_CUDA(s, cudaEventSynchronize(s->snapDone));
     return SF_OK;
 }
+SF_NOTHROW(s, "sf_snapshot_wait")
 
 // ---- checkpoint / restart ------------------------------------------------
 // State = {params, wall particle sets, simulated time, particles {id, position, velocity}}.  A single-GPU run
@@ -1797,7 +1844,7 @@ int checkpoint_load(const char* path, CheckpointData& d)
 } // namespace
 
 int sf_checkpoint_write(sf_solver* s, const char* path, float sim_time)
-{
+try {
     if(!s || !path) return SF_ERR_INVALID;
     if(!s->uploaded) return fail(s, SF_ERR_INVALID, "no particles uploaded");
     try {
@@ -1850,6 +1897,7 @@ int sf_checkpoint_write(sf_solver* s, const char* path, float sim_time)
         return fail(s, SF_ERR_OOM, std::string("sf_checkpoint_write: ") + e.what());
     }
 }
+SF_NOTHROW(s, "sf_checkpoint_write")
 
 static int checkpoint_restore(const char* path, int device, int rank, int nranks, const void* id128, sf_solver** out, float* sim_time)
 {
@@ -1877,19 +1925,21 @@ static int checkpoint_restore(const char* path, int device, int rank, int nranks
 }
 
 int sf_checkpoint_read(const char* path, int device, sf_solver** out, float* sim_time)
-{
+try {
     return checkpoint_restore(path, device, 0, 1, nullptr, out, sim_time);
 }
+SF_NOTHROW(nullptr, "sf_checkpoint_read")
 
 int sf_checkpoint_read_slab(const char* path, int device, int rank, int nranks, const void* id128, sf_solver** out, float* sim_time)
-{
+try {
     if(nranks < 1 || rank < 0 || rank >= nranks || (nranks > 1 && !id128)) return fail(nullptr, SF_ERR_INVALID, "bad rank / nranks / id");
     return checkpoint_restore(path, device, rank, nranks, id128, out, sim_time);
 }
+SF_NOTHROW(nullptr, "sf_checkpoint_read_slab")
 
 // ---- multi-GPU: z-slab decomposition (design notes in sf_slab.cuh) -----------------------------
 int sf_comm_unique_id(void* id128)
-{
+try {
     if(!id128) return SF_ERR_INVALID;
     NcclApi& nc = nccl_api();
     if(!nc.lib || !nc.GetUniqueId) return fail(nullptr, SF_ERR_COMM, "libnccl.so.2 not found");
@@ -1899,9 +1949,10 @@ int sf_comm_unique_id(void* id128)
     std::memcpy(id128, &id, 128);
     return SF_OK;
 }
+SF_NOTHROW(nullptr, "sf_comm_unique_id")
 
 int sf_comm_init(sf_solver* s, int rank, int nranks, const void* id128)
-{
+try {
     if(!s || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return SF_ERR_INVALID;
     if(nranks == 1) return SF_OK;
     NcclApi& nc = nccl_api();
@@ -1929,10 +1980,11 @@ int sf_comm_init(sf_solver* s, int rank, int nranks, const void* id128)
     SF_CUDA(s, cudaMallocHost(reinterpret_cast<void**>(&L.hostTable), sizeof(uint32_t) * kRowWords * nranks));
     return SF_OK;
 }
+SF_NOTHROW(s, "sf_comm_init")
 
 static int upload_particles_global(sf_solver* s, const float* pos_xyz, const float* vel_xyz, uint32_t n_global);
 int sf_upload_particles_global(sf_solver* s, const float* pos_xyz, const float* vel_xyz, uint32_t n_global)
-{
+try {
     if(!s || (!pos_xyz && n_global)) return SF_ERR_INVALID;
     try {
         return upload_particles_global(s, pos_xyz, vel_xyz, n_global);
@@ -1940,6 +1992,7 @@ int sf_upload_particles_global(sf_solver* s, const float* pos_xyz, const float* 
         return fail(s, SF_ERR_OOM, std::string("sf_upload_particles_global: ") + e.what());
     }
 }
+SF_NOTHROW(s, "sf_upload_particles_global")
 
 static int upload_particles_global(sf_solver* s, const float* pos_xyz, const float* vel_xyz, uint32_t n_global)
 {
@@ -2018,7 +2071,7 @@ static int upload_particles_global(sf_solver* s, const float* pos_xyz, const flo
 }
 
 int sf_slab_info(sf_solver* s, int32_t* z_begin, int32_t* z_end, uint32_t* n_owned, uint32_t* n_ghost)
-{
+try {
     if(!s) return SF_ERR_INVALID;
     if(!s->slab.on || s->slab.cur.empty()) {
         if(z_begin) *z_begin = 0;
@@ -2033,6 +2086,7 @@ int sf_slab_info(sf_solver* s, int32_t* z_begin, int32_t* z_end, uint32_t* n_own
     if(n_ghost) *n_ghost = s->n - std::min(s->n, s->slab.nOwn);
     return SF_OK;
 }
+SF_NOTHROW(s, "sf_slab_info")
 
 namespace
 {
@@ -2086,20 +2140,22 @@ int gather_owned(sf_solver* s, uint32_t* ids, float* pos_xyz, float* vel_xyz, ui
 } // namespace
 
 int sf_download_owned(sf_solver* s, uint32_t* ids, float* pos_xyz, float* vel_xyz, uint32_t cap, uint32_t* n_out)
-{
+try {
     if(!s || !n_out) return SF_ERR_INVALID;
     if(!s->uploaded) return fail(s, SF_ERR_INVALID, "no particles uploaded");
     if(!s->ready) return fail(s, SF_ERR_INVALID, "sf_make_ready has not been called");
     SF_CUDA(s, cudaSetDevice(s->device));
     return gather_owned(s, ids, pos_xyz, vel_xyz, cap, n_out);
 }
+SF_NOTHROW(s, "sf_download_owned")
 
 int sf_slab_axis(sf_solver* s, int32_t* axis_out)
-{
+try {
     if(!s || !axis_out) return SF_ERR_INVALID;
     *axis_out = s->axisS;
     return SF_OK;
 }
+SF_NOTHROW(s, "sf_slab_axis")
 
 // Host-owned slab step: the multi-GPU counterpart of sf_step_host.  Between two calls the host holds this rank's
 // OWNED particles {id, position, velocity} (28 B each); the ghost particles of the coming substep stay resident on
@@ -2107,7 +2163,7 @@ int sf_slab_axis(sf_solver* s, int32_t* axis_out)
 // owned particles (the resident copies are dropped), one substep incl. the halo exchange and migration, download
 // the particles this rank owns afterwards (*m_out of them, any order; at most cap are written).
 int sf_step_host_owned(sf_solver* s, uint32_t* ids, float* pos_xyz, float* vel_xyz, uint32_t m_in, uint32_t cap, uint32_t* m_out, float* dt_out)
-{
+try {
     int rc = require_ready(s);
     if(rc) return rc;
     if(!ids || !pos_xyz || !vel_xyz || !m_out) return SF_ERR_INVALID;
@@ -2161,10 +2217,11 @@ int sf_step_host_owned(sf_solver* s, uint32_t* ids, float* pos_xyz, float* vel_x
     if(dt_out) *dt_out = s->hostState->dt;
     return gather_owned(s, ids, pos_xyz, vel_xyz, cap, m_out);
 }
+SF_NOTHROW(s, "sf_step_host_owned")
 
 // raw local state (live + dead slots) <-> host: what bench.py's multi-GPU e2e leg moves every substep
 int sf_download_local(sf_solver* s, float* pos4, float* vel4, uint32_t* ids, uint32_t cap, uint32_t* n_out)
-{
+try {
     if(!s || !n_out) return SF_ERR_INVALID;
     SF_CUDA(s, cudaSetDevice(s->device));
     const uint32_t m = s->slab.on ? s->nSlots : s->n;
@@ -2177,9 +2234,10 @@ int sf_download_local(sf_solver* s, float* pos4, float* vel4, uint32_t* ids, uin
     SF_CUDA(s, cudaStreamSynchronize(s->stream));
     return SF_OK;
 }
+SF_NOTHROW(s, "sf_download_local")
 
 int sf_upload_local(sf_solver* s, const float* pos4, const float* vel4, const uint32_t* ids, uint32_t n)
-{
+try {
     if(!s || !pos4 || !vel4 || !ids) return SF_ERR_INVALID;
     SF_CUDA(s, cudaSetDevice(s->device));
     const uint32_t m = s->slab.on ? s->nSlots : s->n;
@@ -2191,29 +2249,33 @@ int sf_upload_local(sf_solver* s, const float* pos4, const float* vel4, const ui
     SF_CUDA(s, cudaMemcpyAsync(s->B.idA, ids, sizeof(uint32_t) * m, cudaMemcpyHostToDevice, s->stream));
     return SF_OK;
 }
+SF_NOTHROW(s, "sf_upload_local")
 
 // host-side pieces of the decomposition, exposed for tests (no GPU needed)
 int sf_slab_plan(const uint64_t* layer_counts, int32_t nz, int32_t nranks, int32_t* cuts)
-{
+try {
     if(!layer_counts || !cuts || nranks < 1 || nz < nranks * kMinThick) return SF_ERR_INVALID;
     slab_plan(layer_counts, nz, nranks, kMinThick, cuts);
     return SF_OK;
 }
+SF_NOTHROW(nullptr, "sf_slab_plan")
 
 int sf_slab_rebalance(const uint32_t* table, int32_t nranks, int32_t nz, int32_t* cuts)
-{
+try {
     if(!table || !cuts || nranks < 1) return SF_ERR_INVALID;
     slab_rebalance(table, kRowWords, nranks, nz, kMinThick, cuts);
     return SF_OK;
 }
+SF_NOTHROW(nullptr, "sf_slab_rebalance")
 
 int sf_cell_layers(const sf_params* p, const float* pos_xyz, uint32_t n, int32_t* layers)
-{
+try {
     if(!p || (!pos_xyz && n) || !layers) return SF_ERR_INVALID;
     int32_t g[3];
     grid_dims(*p, g);
     for(uint32_t i = 0; i < n; ++i) layers[i] = cell_layer(*p, g[2], pos_xyz[3 * static_cast<size_t>(i) + 2]);
     return SF_OK;
 }
+SF_NOTHROW(nullptr, "sf_cell_layers")
 
 } // extern "C"

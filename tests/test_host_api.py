@@ -131,6 +131,24 @@ def test_product_does_not_reference_oracle():
     assert not bad, bad
 
 
+def test_no_exception_crosses_the_c_boundary():
+    """include/sf_b200.h promises that nothing throws across the boundary: every status-returning entry point with a body
+    of its own is a function-try-block that maps bad_alloc / length_error to SF_ERR_OOM (csrc/sf_api.cu, SF_NOTHROW)."""
+    text = open(os.path.join(ROOT, "simplefluid_b200", "csrc", "sf_api.cu")).read()
+    text = text[text.index('extern "C" {'):]
+    lines = text.split("\n")
+    entries, guarded = [], []
+    for i, line in enumerate(lines):
+        m = re.match(r"^int (sf_\w+)\(.*\)$", line)
+        if m:
+            entries.append(m.group(1))
+            if lines[i + 1] == "try {":
+                guarded.append(m.group(1))
+    assert len(entries) > 40
+    assert entries == guarded, sorted(set(entries) - set(guarded))
+    assert text.count("SF_NOTHROW(") == len(entries) + 1  # + the definition
+
+
 def test_public_header_is_plain_c():
     """include/sf_b200.h is the C-ABI: it must compile as C99 with no C++ or CUDA in sight."""
     import subprocess
