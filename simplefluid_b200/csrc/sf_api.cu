@@ -313,6 +313,7 @@ void fill_dev_params(sf_solver* s)
     P.n    = s->n;
     P.npad = s->npad;
     P.kmax = s->kmax;
+    P.kmaxBytes = static_cast<uint32_t>(s->kmax) * 128u;
     P.nbx  = (s->grid[0] + BX - 1) / BX;
     P.nby  = (s->nM() + BY - 1) / BY;
     P.nbz  = (s->nS() + BZ - 1) / BZ;

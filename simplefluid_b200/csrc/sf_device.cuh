@@ -38,6 +38,7 @@ struct DevParams {
     int   useBoundary, attractive, correctDensity, capture;
     uint32_t n, npad;
     int      kmax;
+    uint32_t kmaxBytes;  // kmax * 128: bytes from the first to one past the last row of a list column
     int      nbx, nby, nbz; // brick grid
     uint32_t numBricks;
     // z-slab decomposition (single GPU: z0 = 0, nzGlobal = nz, every range = [0, nz)).  nz above is the LOCAL
