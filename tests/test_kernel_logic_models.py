@@ -8,7 +8,8 @@ sf_kernels.cuh), operation by operation, checked exhaustively or under random in
     outside the column;
   * the counted exact phase of k_density_brick (non-empty windows pooled per lane, sentinel entry, refill predicated on
     an empty mask, exactly nh iterations): hits come out in ascending (window, slot) order, nothing is evaluated twice,
-    the pool is never indexed beyond its kPool + 2 entries;
+    the pool is never indexed beyond its kPool + 2 entries; and its list position, kept as the bytes left in the
+    column (stores exactly the first kmax rows, counts every accepted pair even past the capacity);
   * count_into_cell (warp-aggregated arrival ranks of the counting sort, also run by the integrate kernel): the ranks
     of the particles of a cell are a permutation of 0 .. count-1 whatever the order in which the warps arrive, and the
     scatter they drive is a bijection onto the sorted slots.
@@ -183,6 +184,41 @@ def test_counted_exact_phase_walks_the_hits_in_traversal_order():
         want = [b + i for m, b in zip(masks, bases) for i in range(32) if m >> i & 1]
         got = counted_exact_phase_model(masks, bases, self_slot)
         assert got == want
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def list_countdown_model(passes, kmax, column_base):
+    """The list position of the density pass's exact phase (SF_HIT_STEP): ko = bytes LEFT in the column as a 32-bit
+    register, the store goes to (column end - ko) when the pair passes and (int32)ko > 0, and ko drops by 128 (one
+    row) per accepted pair -- also beyond the capacity, where it wraps below zero.  Returns (stored addresses,
+    accepted pairs recovered from ko, address of the next row)."""
+    M = 0xFFFFFFFF
+    kmax_bytes = kmax * 128
+    ko = kmax_bytes
+    lpe = column_base + kmax_bytes
+    stored = []
+    for p in passes:
+        signed = ko - (1 << 32) if ko & 0x80000000 else ko
+        if p and signed > 0:
+            stored.append(lpe - ko)
+        if p:
+            ko = (ko + ((-128) & M)) & M
+    words = ((kmax_bytes - ko) & M) >> 2
+    return stored, words // 32, column_base + 4 * words
+
+
+@pytest.mark.parametrize("kmax", [8, 28, 64, 16380])
+def test_list_countdown_stores_the_first_kmax_rows_and_counts_every_pair(kmax):
+    rng = random.Random(kmax)
+    base = 0x7F0000001000
+    for trial in range(200):
+        n = rng.choice([0, 1, kmax - 1, kmax, kmax + 1, 2 * kmax + 3, rng.randrange(0, 3 * kmax)])
+        passes = [rng.random() < 0.8 for _ in range(n)]
+        stored, accepted, next_row = list_countdown_model(passes, kmax, base)
+        a = sum(passes)
+        assert accepted == a                                            # the count survives the overflow (fits = k <= kmax)
+        assert stored == [base + 128 * r for r in range(min(a, kmax))]  # rows 0 .. kmax-1 in order, nothing past the column
+        assert next_row == base + 128 * a                               # where the wall rows continue (only used when a < kmax)
 
 
 # ---------------------------------------------------------------------------------------------------------------
