@@ -6,6 +6,9 @@ sf_kernels.cuh), operation by operation, checked exhaustively or under random in
   * walk_list: the software pipeline of the list walkers (rows requested unconditionally inside the column, two register
     sets, tail without a further request) visits the first nF entries exactly once, in order, and never reads a row
     outside the column;
+  * phase A of k_density_brick (quad-aligned filter reads, miss bits shifted into place by the funnel shift, range and
+    self masks with PTX shift semantics): a window's mask reports exactly the filter hits of the lane's own run, in
+    slot order, never the particle itself, whatever the run lengths and alignments of the other lanes of the warp;
   * the counted exact phase of k_density_brick (non-empty windows pooled per lane, sentinel entry, refill predicated on
     an empty mask, exactly nh iterations): hits come out in ascending (window, slot) order, nothing is evaluated twice,
     the pool is never indexed beyond its kPool + 2 entries; and its list position, kept as the bytes left in the
@@ -184,6 +187,92 @@ def test_counted_exact_phase_walks_the_hits_in_traversal_order():
         want = [b + i for m, b in zip(masks, bases) for i in range(32) if m >> i & 1]
         got = counted_exact_phase_model(masks, bases, self_slot)
         assert got == want
+
+
+# ---------------------------------------------------------------------------------------------------------------
+M32 = 0xFFFFFFFF
+
+
+def shl_clamp(a, n):
+    """PTX shl.b32: shift amounts above 31 give 0 (n is an unsigned 32-bit register)."""
+    n &= M32
+    return (a << n) & M32 if n < 32 else 0
+
+
+def filter_quads_model(miss, addr, nq):
+    """filter_quads of sf_pairs.cuh with the half-precision arithmetic replaced by an oracle `miss(slot)`: the MISS bits
+    of nq quads starting at halo slot `addr` in the top 4 * nq bits (first quad lowest), zeros below; also returns the
+    slots read."""
+    mask, read = 0, []
+    for q in range(nq):
+        nb = 0
+        for i in range(4):
+            read.append(addr + 4 * q + i)
+            nb |= (1 if miss(addr + 4 * q + i) else 0) << (28 + i)
+        mask = (mask >> 4) | nb
+    return mask, read
+
+
+def window_masks_model(lanes, hit):
+    """Phase A of k_density_brick for one halo row of one warp.  lanes: (jbase, length, self_slot) per lane -- the
+    lane's candidate run and its own halo slot; hit(lane, slot): what the conservative filter says.  Returns, per lane,
+    the (mask, first slot) of every window, exactly as pushed to the pool, and checks that no quad load starts before
+    the lane's quad-aligned run start or runs more than one quad past what the widest lane needs."""
+    pre = [jb - (jb & ~3) for jb, _, _ in lanes]
+    maxlen = max(ln for _, ln, _ in lanes)
+    maxend = max((p + ln if ln else 0) for p, (_, ln, _) in zip(pre, lanes))
+    out = [[] for _ in lanes]
+    c0 = 0
+    while c0 < maxlen:
+        quads = (min(maxend - c0, 35) + 3) >> 2  # warp-uniform
+        assert 1 <= quads <= 9
+        nq_lo = min(quads, 8)
+        for li, (jbase, ln, self_slot) in enumerate(lanes):
+            a0 = jbase & ~3
+            addr = a0 + c0
+            miss = lambda slot: not hit(li, slot)  # noqa: E731
+            lo, read = filter_quads_model(miss, addr, nq_lo)
+            hi = 0
+            if quads > 8:
+                h, r2 = filter_quads_model(miss, addr + 32, 1)
+                hi = h >> 28
+                read += r2
+            assert min(read) == addr and max(read) < addr + 4 * quads
+            lo >>= 4 * (8 - nq_lo)
+            mask = ~(((hi << 32) | lo) >> pre[li]) & M32  # ~__funnelshift_r(lo, hi, pre)
+            vlen = max(ln - c0, 0)
+            mask &= ~shl_clamp(M32, vlen) & M32
+            mask &= ~shl_clamp(1, (self_slot - (jbase + c0)) & M32) & M32
+            # every slot the mask may report was actually read
+            for i in range(32):
+                if mask >> i & 1:
+                    assert jbase + c0 + i in read
+            out[li].append((mask, jbase + c0))
+        c0 += 32
+    return out
+
+
+def test_window_masks_report_exactly_the_filter_hits_of_the_lanes_own_run():
+    rng = random.Random(11)
+    for trial in range(400):
+        nl = rng.choice([1, 4, 32])
+        lanes = []
+        for _ in range(nl):
+            ln = rng.choice([0, 1, 3, 17, 26, 31, 32, 33, 35, 36, 40, 56, 64, 65, 100])
+            jbase = rng.randrange(0, 3000)
+            self_slot = rng.choice([jbase + rng.randrange(0, max(ln, 1)), jbase - 5 if jbase >= 5 else jbase + ln + 7, rng.randrange(0, 3584)])
+            lanes.append((jbase, ln, self_slot))
+        density = rng.choice([0.0, 0.15, 0.6, 1.0])
+        table = {}
+
+        def hit(li, slot):
+            return table.setdefault((li, slot), rng.random() < density)
+
+        got = window_masks_model(lanes, hit)
+        for li, (jbase, ln, self_slot) in enumerate(lanes):
+            slots = [b + i for m, b in got[li] for i in range(32) if m >> i & 1]
+            want = [sl for sl in range(jbase, jbase + ln) if sl != self_slot and hit(li, sl)]
+            assert slots == want, (trial, li, lanes[li])
 
 
 # ---------------------------------------------------------------------------------------------------------------
