@@ -81,6 +81,14 @@ int sf_scene_generate(const sf_params* p, int scene, float* pos_xyz, uint64_t ca
 int sf_build_tables(const sf_params* p, float* cubic_w10001, float* spiky_grad10001, float* consts3);
 /* generateBoundaryParticles (EXE@0x140016d80) for one wall with an explicit seed. */
 int sf_boundary_generate(const sf_params* p, uint32_t seed, int wall, float* xyz, uint32_t cap, uint32_t* n_out);
+/* Candidate masks of a wall list, as the density pass uses them (no counterpart in the reference, whose loop
+ * over a wall list -- EXE@0x1400179c0, SURVEY A.6 -- tests all of its particles): masks[(SF_WALL_SUBCELLS + 1) * words],
+ * words >= (n + 31) / 32; bit b of entry c marks wall particle b as possibly within h of sub-cell c of the h-cube a
+ * shifted near-wall position lies in; entry SF_WALL_SUBCELLS marks every particle.  sf_wall_subcell: the entry a
+ * position takes (same fp32 operations as the device).  Exposed so that the bound can be checked without a GPU. */
+#define SF_WALL_SUBCELLS 64
+int sf_wall_candidate_masks(const sf_params* p, int wall, const float* xyz, uint32_t n, uint32_t words, uint32_t* masks);
+int sf_wall_subcell(const sf_params* p, int wall, const float pos_xyz[3], uint32_t* entry_out);
 
 /* ---- lifecycle: QtSPHSolver ctor/dtor (Include/QtSPHSolver.h:30-31) ------------------------- */
 int  sf_create(const sf_params* p, int device, sf_solver** out);

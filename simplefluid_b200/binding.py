@@ -18,7 +18,7 @@ FIELD_DENSITY, FIELD_PRESSURE, FIELD_ACCEL, FIELD_CELL_INDEX, FIELD_NEIGHBOR_COU
 
 EXPORTS = [
     "sf_params_default", "sf_params_set_resolution", "sf_params_update", "sf_scene_generate", "sf_build_tables",
-    "sf_boundary_generate", "sf_create", "sf_destroy",
+    "sf_boundary_generate", "sf_wall_candidate_masks", "sf_wall_subcell", "sf_create", "sf_destroy",
     "sf_set_params", "sf_get_params", "sf_last_error", "sf_set_stream", "sf_upload_particles", "sf_num_particles",
     "sf_download_positions", "sf_download_velocities", "sf_generate_boundary", "sf_set_boundary_particles",
     "sf_get_boundary_particles", "sf_make_ready", "sf_advance_frame", "sf_advance_steps", "sf_advance_frame_time",
@@ -89,6 +89,7 @@ def library():
         "sf_params_default": [PP], "sf_params_set_resolution": [PP, f32], "sf_params_update": [PP],
         "sf_scene_generate": [PP, C.c_int, vp, u64, C.POINTER(u64)],
         "sf_build_tables": [PP, vp, vp, vp], "sf_boundary_generate": [PP, u32, C.c_int, vp, u32, C.POINTER(u32)],
+        "sf_wall_candidate_masks": [PP, C.c_int, vp, u32, u32, vp], "sf_wall_subcell": [PP, C.c_int, vp, C.POINTER(u32)],
         "sf_create": [PP, C.c_int, C.POINTER(vp)], "sf_set_params": [vp, PP], "sf_get_params": [vp, PP],
         "sf_set_stream": [vp, vp], "sf_upload_particles": [vp, vp, vp, u32], "sf_num_particles": [vp, C.POINTER(u32)],
         "sf_download_positions": [vp, vp], "sf_download_velocities": [vp, vp], "sf_generate_boundary": [vp, u32],
@@ -190,6 +191,29 @@ def boundary_generate(params, seed, wall):
     out = np.empty((n.value, 3), np.float32)
     library().sf_boundary_generate(C.byref(params), seed, wall, out.ctypes.data, n.value, C.byref(n))
     return out
+
+
+WALL_SUBCELLS = 64
+
+
+def wall_candidate_masks(params, wall, xyz):
+    """Candidate masks of a wall list as the density pass uses them: (WALL_SUBCELLS + 1, words) uint32."""
+    xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+    words = max((len(xyz) + 31) // 32, 1)
+    out = np.zeros((WALL_SUBCELLS + 1, words), np.uint32)
+    rc = library().sf_wall_candidate_masks(C.byref(params), wall, xyz.ctypes.data, len(xyz), words, out.ctypes.data)
+    if rc:
+        raise SFError(rc, "sf_wall_candidate_masks: invalid arguments")
+    return out
+
+
+def wall_subcell(params, wall, pos):
+    pos = np.ascontiguousarray(pos, np.float32).reshape(3)
+    e = C.c_uint32(0)
+    rc = library().sf_wall_subcell(C.byref(params), wall, pos.ctypes.data, C.byref(e))
+    if rc:
+        raise SFError(rc, "sf_wall_subcell: invalid arguments")
+    return e.value
 
 
 def comm_unique_id():

@@ -326,6 +326,8 @@ void fill_dev_params(sf_solver* s)
     P.slab  = 0;
     for(int w = 0; w < 6; ++w) P.nbnd[w] = P.useBoundary ? static_cast<uint32_t>(s->walls[w].size() / 3) : 0u;
     P.bndStride = s->bndStride;
+    P.wallWords  = (s->bndStride + 31u) / 32u;
+    P.wallSubInv = wall_sub_inv(p);
 }
 
 // preserve > 0: the first `preserve` slots of the state arrays (posA / velA / idA) survive the reallocation; every
@@ -833,6 +835,23 @@ try {
 }
 SF_NOTHROW(nullptr, "sf_boundary_generate")
 
+int sf_wall_candidate_masks(const sf_params* p, int wall, const float* xyz, uint32_t n, uint32_t words, uint32_t* masks)
+try {
+    if(!p || wall < 0 || wall > 5 || (!xyz && n) || !masks || words < (n + 31u) / 32u) return SF_ERR_INVALID;
+    static_assert(SF_WALL_SUBCELLS == kWallSubCells, "public constant follows the internal one");
+    wall_candidate_masks(*p, wall, xyz, n, words, masks);
+    return SF_OK;
+}
+SF_NOTHROW(nullptr, "sf_wall_candidate_masks")
+
+int sf_wall_subcell(const sf_params* p, int wall, const float pos_xyz[3], uint32_t* entry_out)
+try {
+    if(!p || wall < 0 || wall > 5 || !pos_xyz || !entry_out) return SF_ERR_INVALID;
+    *entry_out = static_cast<uint32_t>(wall_subcell(*p, wall, pos_xyz));
+    return SF_OK;
+}
+SF_NOTHROW(nullptr, "sf_wall_subcell")
+
 int sf_create(const sf_params* p, int device, sf_solver** out)
 try {
     if(!p || !out) return fail(nullptr, SF_ERR_INVALID, "null argument");
@@ -894,7 +913,7 @@ void sf_destroy(sf_solver* s)
     cudaFree(B.posA); cudaFree(B.velA); cudaFree(B.posB); cudaFree(B.velB); cudaFree(B.idA); cudaFree(B.idB);
     for(int i = 0; i < 2; ++i) { cudaFree(B.keys[i]); cudaFree(B.vals[i]); }
     cudaFree(B.cellTab); cudaFree(B.cellCnt); cudaFree(B.rho); cudaFree(B.rho2); cudaFree(B.accel); cudaFree(B.nbrL); cudaFree(B.nbrCnt); cudaFree(B.brickFlag); cudaFree(B.brickList);
-    cudaFree(B.tabW); cudaFree(B.tabG); cudaFree(B.bnd); cudaFree(B.radixCounts); cudaFree(B.radixTotals); cudaFree(B.state);
+    cudaFree(B.tabW); cudaFree(B.tabG); cudaFree(B.bnd); cudaFree(B.wallMask); cudaFree(B.radixCounts); cudaFree(B.radixTotals); cudaFree(B.state);
     cudaFree(s->stage);
     cudaFree(s->cellTileSums);
     if(s->xferStream) {
@@ -1118,6 +1137,15 @@ try {
             bnd[static_cast<size_t>(w) * s->bndStride + b] = make_float4(s->walls[w][3 * b], s->walls[w][3 * b + 1], s->walls[w][3 * b + 2], 0.f);
     SF_CUDA(s, dev_alloc(s->B.bnd, bnd.size()));
     SF_CUDA(s, cudaMemcpyAsync(s->B.bnd, bnd.data(), sizeof(float4) * bnd.size(), cudaMemcpyHostToDevice, s->stream));
+    {   // candidate masks of the wall lists for the density pass (sf_host.cpp: wall_candidate_masks)
+        const uint32_t        words = (s->bndStride + 31u) / 32u;
+        const size_t          perWall = static_cast<size_t>(kWallSubCells + 1) * words;
+        std::vector<uint32_t> masks(6 * perWall, 0u);
+        for(int w = 0; w < 6; ++w)
+            wall_candidate_masks(s->params, w, s->walls[w].data(), static_cast<uint32_t>(s->walls[w].size() / 3), words, masks.data() + w * perWall);
+        SF_CUDA(s, dev_alloc(s->B.wallMask, masks.size()));
+        SF_CUDA(s, cudaMemcpy(s->B.wallMask, masks.data(), sizeof(uint32_t) * masks.size(), cudaMemcpyHostToDevice)); // (synchronous: `masks` is a local)
+    }
 
     // radix-sort plan: ceil(log2(ncells)) key bits in passes of at most 8 bits
     int bits = 1;

@@ -57,6 +57,8 @@ struct DevParams {
     int      axisS;
     uint32_t nbnd[6];     // wall particle counts
     uint32_t bndStride;   // slots per wall in the bnd array
+    uint32_t wallWords;   // words per candidate mask of a wall list (wallMask)
+    float    wallSubInv;  // kWallSub / h: sub-cell index of a shifted near-wall position (host: wall_sub_inv)
 };
 
 struct DevState {
@@ -96,6 +98,7 @@ struct DevBuffers {
     uint32_t* brickList;
     float *tabW, *tabG;   // kTableEntries each
     float4*   bnd;        // [6][bndStride]
+    uint32_t* wallMask;   // [6][kWallSubCells + 1][wallWords]: wall particles that can be within h of a sub-cell (sf_host.cpp)
     uint32_t* radixCounts;
     uint32_t* radixTotals;
     DevState* state;

@@ -10,6 +10,7 @@
 //   Grid3D::setGrid                           EXE@0x14001ab20
 //   SPHSolver::generateBoundaryParticles      EXE@0x140016d80
 #include "sf_internal.h"
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <random>
@@ -342,5 +343,57 @@ void generate_boundary(const sf_params& p, uint32_t seed, std::vector<float> wal
             }
         }
     }
+}
+// ------------------------------------------------------------------------------------------------
+// Candidate masks of the wall particles (density pass).  The reference tests every particle of a wall list against
+// every near-wall fluid particle (243 per wall with the generated walls, of which about 9 are within h).  A fluid
+// particle within h of wall w meets the list through its SHIFTED position (A.6): the two tangential coordinates
+// wrapped into [0, h), the normal coordinate within h of the wall plane -- a cube of edge h.  That cube is cut into
+// kWallSub^3 sub-cells, and for each sub-cell the wall particles that can be within h of SOME point of it are marked
+// in a bit mask (bit b of word b / 32 = wall particle b): the density pass walks the set bits of its sub-cell's mask
+// in ascending order -- the list order -- and applies the exact test to each, so sums, list entries and their order
+// are those of the full loop.  Works for any wall list (sf_set_boundary_particles), not only the generated ones.
+// Conservative by construction: the sub-cell boxes overlap by 1 % of h (the device derives the sub-cell from its
+// own fp32 shifted position; its rounding is eight orders of magnitude below that), the distance bound carries a
+// relative 1e-4, and positions beyond the wall plane (possible for an upload in the last, partly outside, cell
+// layer) take entry kWallSubCells: every particle of the list.
+int wall_subcell(const sf_params& p, int wall, const float x[3])
+{
+    const int   A = wall / 2, t1 = A == 0 ? 1 : 0, t2 = A == 2 ? 1 : 2;
+    const float h = p.kernelRadius, inv = wall_sub_inv(p);
+    const float s1 = x[t1] - h * std::floor(x[t1] / h), s2 = x[t2] - h * std::floor(x[t2] / h); // wall_shift
+    const float dn = (wall & 1) ? p.boxMax[A] - x[A] : x[A] - p.boxMin[A];
+    if(dn < 0.0f) return kWallSubCells;
+    auto idx = [inv](float v) {
+        const int i = static_cast<int>(std::floor(v * inv));
+        return i < 0 ? 0 : (i > kWallSub - 1 ? kWallSub - 1 : i);
+    };
+    return (idx(dn) * kWallSub + idx(s2)) * kWallSub + idx(s1);
+}
+
+float wall_sub_inv(const sf_params& p) { return static_cast<float>(kWallSub) / p.kernelRadius; }
+
+void wall_candidate_masks(const sf_params& p, int wall, const float* xyz, uint32_t n, uint32_t words, uint32_t* masks)
+{
+    const int    A = wall / 2, t1 = A == 0 ? 1 : 0, t2 = A == 2 ? 1 : 2;
+    const double h = p.kernelRadius, inv = wall_sub_inv(p), m = 0.01 * h, reach = h * (1.0 + 1e-4);
+    const double wallPlane = (wall & 1) ? p.boxMax[A] : p.boxMin[A], sgn = (wall & 1) ? -1.0 : 1.0;
+    std::fill(masks, masks + static_cast<size_t>(kWallSubCells + 1) * words, 0u);
+    for(uint32_t b = 0; b < n; ++b) masks[static_cast<size_t>(kWallSubCells) * words + b / 32u] |= 1u << (b % 32u);
+    auto gap = [](double q, double lo, double hi) { return q < lo ? lo - q : (q > hi ? q - hi : 0.0); };
+    for(int in = 0; in < kWallSub; ++in)
+        for(int i2 = 0; i2 < kWallSub; ++i2)
+            for(int i1 = 0; i1 < kWallSub; ++i1) {
+                uint32_t* mk = masks + static_cast<size_t>((in * kWallSub + i2) * kWallSub + i1) * words;
+                // normal coordinate: distance dn from the wall plane into the box, absolute position = plane + sgn * dn
+                const double nLoD = in / inv - m, nHiD = (in + 1) / inv + m;
+                const double nLo = sgn > 0 ? wallPlane + nLoD : wallPlane - nHiD, nHi = sgn > 0 ? wallPlane + nHiD : wallPlane - nLoD;
+                for(uint32_t b = 0; b < n; ++b) {
+                    const double g1 = gap(xyz[3 * b + t1], i1 / inv - m, (i1 + 1) / inv + m);
+                    const double g2 = gap(xyz[3 * b + t2], i2 / inv - m, (i2 + 1) / inv + m);
+                    const double gn = gap(xyz[3 * b + A], nLo, nHi);
+                    if(g1 * g1 + g2 * g2 + gn * gn <= reach * reach) mk[b / 32u] |= 1u << (b % 32u);
+                }
+            }
 }
 } // namespace sf

@@ -28,6 +28,12 @@ void grid_dims(const sf_params& p, int32_t n[3]);
 // unclamped cell coordinates of a position (A.6); returns false if outside the grid / not finite
 bool cell_coords_checked(const sf_params& p, const int32_t n[3], const float* x, int32_t c[3]);
 void generate_boundary(const sf_params& p, uint32_t seed, std::vector<float> walls[6]);
+// Candidate masks of a wall list for the density pass (see sf_host.cpp): [kWallSubCells + 1][words] words, bit b = wall
+// particle b; wall_subcell is the host mirror of the device's sub-cell index (same fp32 operations)
+constexpr int kWallSub = 4, kWallSubCells = kWallSub * kWallSub * kWallSub;
+float wall_sub_inv(const sf_params& p);
+int   wall_subcell(const sf_params& p, int wall, const float x[3]);
+void  wall_candidate_masks(const sf_params& p, int wall, const float* xyz, uint32_t n, uint32_t words, uint32_t* masks);
 // global cell layer (A.7 z index, clamped) of a z coordinate -- same float ops as the device hash
 int32_t cell_layer(const sf_params& p, int32_t n, float coord, int axis = 2);
 // z-slab decomposition (no counterpart in the reference): count-balanced cut planes with a minimum thickness, and

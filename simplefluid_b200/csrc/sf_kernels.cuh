@@ -9,6 +9,7 @@
 #pragma once
 #include <cfloat>
 #include "sf_device.cuh"
+#include "sf_internal.h"
 
 namespace sf
 {
@@ -66,6 +67,19 @@ __device__ __forceinline__ int wall_of(const DevParams& P, const float4& x)
     if(lo > xa) return 2 * A;
     if(xa > hi) return 2 * A + 1;
     return -1;
+}
+
+// Sub-cell of the h-cube a shifted near-wall position lies in -> entry of the wall's candidate masks (sf_host.cpp:
+// wall_subcell is the host mirror, wall_candidate_masks builds the masks).  xs = wall_shift<A>(P, x), w = wall_of<A>.
+template<int A>
+__device__ __forceinline__ uint32_t wall_subcell(const DevParams& P, const float4& x, const float3& xs, int w)
+{
+    const float dn = (w & 1) ? P.bmax[A] - comp(x, A) : comp(x, A) - P.bmin[A];
+    const float s1 = A == 0 ? xs.y : xs.x, s2 = A == 2 ? xs.y : xs.z;
+    const int   i1 = min(max(__float2int_rd(s1 * P.wallSubInv), 0), kWallSub - 1);
+    const int   i2 = min(max(__float2int_rd(s2 * P.wallSubInv), 0), kWallSub - 1);
+    const int   in = min(max(__float2int_rd(dn * P.wallSubInv), 0), kWallSub - 1);
+    return dn < 0.0f ? static_cast<uint32_t>(kWallSubCells) : static_cast<uint32_t>((in * kWallSub + i2) * kWallSub + i1);
 }
 
 // ------------------------------------------------------------------------------------------------
