@@ -149,6 +149,23 @@ def test_no_exception_crosses_the_c_boundary():
     assert text.count("SF_NOTHROW(") == len(entries) + 1  # + the definition
 
 
+def test_every_entry_point_rejects_a_null_solver(sf):
+    """The reference Q_ASSERTs on a null solver (Source/Simulator.cpp:35-36); the C-ABI returns SF_ERR_INVALID from every
+    entry point that takes one -- before touching CUDA, so this runs without a GPU."""
+    hdr = open(os.path.join(ROOT, "include", "sf_b200.h")).read()
+    entries = re.findall(r"^int\s+(sf_\w+)\(sf_solver\* s([^)]*)\)", hdr, re.M)
+    assert len(entries) >= 40
+    L = C.CDLL(sf.library_path())
+    for name, rest in entries:
+        fn = getattr(L, name)
+        fn.restype = C.c_int
+        fn.argtypes = None
+        args = []
+        for a in [a.strip() for a in rest.split(",") if a.strip()]:
+            args.append(C.c_double(0.0) if a.startswith("double") else (C.c_float(0.0) if a.startswith("float ") else C.c_void_p(0)))
+        assert fn(None, *args) == -1, name
+
+
 def test_public_header_is_plain_c():
     """include/sf_b200.h is the C-ABI: it must compile as C99 with no C++ or CUDA in sight."""
     import subprocess
